@@ -12,7 +12,8 @@
  *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. PyTorch tensors);
  *     "host" pointers are ordinary host memory.  The library owns all emulator state.
  *   - a handle is bound to one CUDA device; calls are ordered on the `stream` argument
- *     (a cudaStream_t passed as void*, NULL = the handle's own stream) and asynchronous with
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream, which is what PyTorch
+ *     uses by default; the handle's internal stream is a blocking stream ordered with it) and asynchronous with
  *     respect to the host unless stated otherwise.  Not re-entrant per handle.
  *   - there is NO CPU fallback: gbenv_create fails with GBENV_E_CUDA when no device is usable.
  *

@@ -1,0 +1,158 @@
+// gb_kernels.cuh -- emulation kernels: the 24-frame step, state scatter/gather, bus access.
+#pragma once
+#include "gb_device.cuh"
+
+#define STEP_THREADS 128
+
+// pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
+// (Right Left Up Down A B Select Start, the bit order of PyBoy's Interaction nibbles)
+__constant__ int c_action_button[8] = {3, 1, 0, 2, 4, 5, 7, 6};
+
+struct RunParams {
+    DevArrays d;
+    const uint8_t *actions;  // may be null: plain ticks without input
+    int n_frames;
+    int render_mode;  // 0: renderer disabled, 1: enabled on every frame, 2: enabled on the last frame only
+    int release_frame;  // frame index at which the button is released (8 in the reference)
+    unsigned long long *counters;  // [0] instructions, [1] cycles, [2] frames, [3] faults
+};
+
+// One thread per env, one warp per 32-env tile.  Runs `n_frames` whole frames without returning to the
+// host (pyboy_binding.run_action_on_emulator :71-91).  The loop is organised around LCD events: the
+// inner do-while interprets instructions until this env's LCD clock reaches its next mode change, the
+// outer body performs the mode change (scanline parameters, rendering, LY/STAT/interrupt flags).  All
+// envs see the same number of LCD events per frame, so the warp re-converges 442 times a frame and
+// the scanline renderer runs with all 32 lanes active.
+__global__ void __launch_bounds__(STEP_THREADS) k_run_frames(RunParams p) {
+    __shared__ uint32_t s_line[FB_LINE_WORDS * STEP_THREADS];
+    __shared__ uint32_t s_keys[10 * STEP_THREADS];
+    const int tid = threadIdx.x;
+    const int tile = (blockIdx.x * STEP_THREADS + tid) >> 5, lane = tid & 31;
+    const int env = tile * GB_TILE + lane;
+    if (tile >= p.d.n_tiles || env >= p.d.n_envs) return;
+    uint32_t *line = s_line + tid, *keys = s_keys + tid;
+    const uint32_t ls = STEP_THREADS;
+
+    Machine m;
+    machine_load(m, p.d, tile, lane);
+    const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
+
+    for (int frame = 0; frame < p.n_frames; frame++) {
+        // PyBoy.tick applies queued inputs before Motherboard.tick
+        if (button >= 0) {
+            if (frame == 0) joypad_event(m, button, 1);
+            if (frame == p.release_frame) joypad_event(m, button, 0);
+        }
+        m.disable_renderer = p.render_mode == 1 ? 0 : p.render_mode == 2 ? (frame != p.n_frames - 1) : 1;
+        // Motherboard.tick: while lcd.processing_frame()
+        bool done = m.frame_done;
+        m.frame_done = 0;
+        while (!done) {
+            bool event;
+            do {
+                uint32_t cycles = cpu_tick(m);
+                if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
+                    int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
+                    int c = a < b ? a : b;
+                    cycles = c < 0 ? 0 : (uint32_t)c;
+                }
+                m.n_cycles += cycles;
+                timer_tick(m, cycles);
+                m.clock += cycles;
+                event = (m.lcdc & 0x80) ? (m.clock >= m.target) : (m.clock >= FRAME_CYCLES);
+            } while (!event);
+            lcd_event(m, line, keys, ls);
+            done = m.frame_done;
+            m.frame_done = 0;
+        }
+    }
+    machine_store(m, p.d, tile, lane);
+    if (p.counters) {
+        atomicAdd(&p.counters[0], (unsigned long long)m.n_instr);
+        atomicAdd(&p.counters[1], (unsigned long long)m.n_cycles);
+        atomicAdd(&p.counters[2], (unsigned long long)p.n_frames);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canonical per-env image <-> interleaved arrays.  image word j of env e lives at:
+//   IMG_MEM..: mem, IMG_CRAM..: cram, IMG_FB..: fb, IMG_LP..: lp (pair-interleaved), IMG_REGS..: regs
+__device__ __forceinline__ uint32_t *image_slot(const DevArrays &d, int env, uint32_t j) {
+    int tile = env >> 5, lane = env & 31;
+    if (j < IMG_CRAM) return d.mem + il_index(tile, MEM_WORDS, j - IMG_MEM, lane);
+    if (j < IMG_FB) return d.cram + il_index(tile, CRAM_WORDS, j - IMG_CRAM, lane);
+    if (j < IMG_LP) return d.fb + il_index(tile, FB_WORDS, j - IMG_FB, lane);
+    if (j < IMG_REGS) return d.lp + lp_index(tile, j - IMG_LP, lane);
+    return d.regs + il_index(tile, R_WORDS, j - IMG_REGS, lane);
+}
+
+// PyBoy load_state semantics that depend on the env's previous state (oracle GBQ_STAT_LOAD_KEEPS_MODE):
+// STAT bits 0-2 and STATRegister._mode survive a load; LCD-off states force mode 0 through set_lcdc.
+// For v7 blobs clock / clock_target / next_stat_mode / IF / interrupt_queued are not in the file.
+__device__ __forceinline__ uint32_t merge_loaded_reg(uint32_t r, uint32_t old, uint32_t neu, int version, uint32_t new_lcdc) {
+    if (version == 0) return neu;  // raw image (power-on): no PyBoy load_state semantics
+    bool lcd_off = !(new_lcdc & 0x80);
+    if (r == R_LCD0) {
+        uint32_t old_stat = (old >> 8) & 0xFF;
+        if (lcd_off) old_stat &= 0xFC;  // set_lcdc -> STAT.set_mode(0)
+        uint32_t stat = (old_stat & 0x87) | ((neu >> 8) & 0x78);
+        return (neu & 0xFFFF00FFu) | (stat << 8);
+    }
+    if (r == R_LCD2) {
+        uint32_t oldf = old >> 24, mode = oldf & 3, next = (neu >> 26) & 3;
+        if (lcd_off) mode = 0;
+        if (version < 8) next = lcd_off ? 2 : ((oldf >> 2) & 3);
+        return (neu & 0x00FFFFFFu) | ((mode | (next << 2) | (oldf & 0x30)) << 24);
+    }
+    if (r == R_JOY) return (neu & 0xFF00FFFFu) | (old & 0x00FF0000u);  // Renderer.ly_window is not serialised
+    if (version < 8) {
+        if (r == R_CLOCK) return lcd_off ? 0 : old;
+        if (r == R_TARGET) return lcd_off ? FRAME_CYCLES : old;
+        if (r == R_INT) return (neu & 0x0000FF17u) | (old & 0x00FF0008u);  // keep IF and interrupt_queued
+    }
+    return neu;
+}
+
+// grid: (ceil(n / 32), ceil(IMG_WORDS / 8)); block (32, 8): x = env slot (coalesced), y = image word
+__global__ void k_scatter_image(DevArrays d, const uint32_t *image, const int32_t *env_ids, int n, int version) {
+    int i = blockIdx.x * 32 + threadIdx.x;
+    uint32_t j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= n || j >= IMG_WORDS) return;
+    int env = env_ids ? env_ids[i] : i;
+    uint32_t v = image[j];
+    uint32_t *slot = image_slot(d, env, j);
+    if (j >= IMG_REGS) v = merge_loaded_reg(j - IMG_REGS, *slot, v, version, image[IMG_REGS + R_LCD0] & 0xFF);
+    *slot = v;
+}
+
+__global__ void k_gather_image(DevArrays d, uint32_t *image, int env) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < IMG_WORDS) image[j] = *image_slot(d, env, j);
+}
+
+// PyBoy.get_memory_value / set_memory_value for one env: full bus semantics incl. IO side effects
+__global__ void k_bus_access(DevArrays d, int env, uint32_t addr, uint32_t n, uint8_t *buf, int write) {
+    if (threadIdx.x || blockIdx.x) return;
+    Machine m;
+    machine_load(m, d, env >> 5, env & 31);
+    for (uint32_t i = 0; i < n; i++) {
+        if (write) bus_write(m, (addr + i) & 0xFFFF, buf[i]);
+        else buf[i] = (uint8_t)bus_read(m, (addr + i) & 0xFFFF);
+    }
+    if (write) machine_store(m, d, env >> 5, env & 31);
+}
+
+// PyBoy.send_input applied to every env at once (Interaction.key_event + IF bit 4 on a 1->0 edge)
+__global__ void k_send_input(DevArrays d, int button, int pressed) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= d.n_envs) return;
+    int tile = env >> 5, lane = env & 31;
+    uint32_t *rj = d.regs + il_index(tile, R_WORDS, R_JOY, lane), *ri = d.regs + il_index(tile, R_WORDS, R_INT, lane);
+    uint32_t w = *rj, dir = w & 0xFF, std_ = (w >> 8) & 0xFF;
+    uint32_t bit = 1u << (button & 3);
+    uint32_t &reg = button < 4 ? dir : std_;
+    uint32_t before = reg;
+    reg = pressed ? (reg & ~bit) : (reg | bit);
+    if ((before ^ reg) & before) *ri |= IRQ_JOYPAD << 16;
+    *rj = (w & 0xFFFF0000u) | dir | (std_ << 8);
+}
