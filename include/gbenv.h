@@ -63,6 +63,9 @@ const char *gbenv_last_error(const gbenv_t *h);
 int gbenv_num_envs(const gbenv_t *h);
 int gbenv_abi_version(void);
 int gbenv_sync(gbenv_t *h); /* cudaStreamSynchronize on the handle's stream */
+/* Tuning knob: envs carried by each warp of the emulation kernel (power of two, 1..32).  The default is
+ * chosen from n_envs and the SM count so that a small batch still fills the GPU with warps.        */
+int gbenv_set_lanes_per_warp(gbenv_t *h, int lanes);
 
 /* ---- (4) reset from PyBoy .state files ------------------------------------------------------
  * replaces pyboy_binding.open_state_file / load_pyboy_state (:59-69).  A blob is parsed ONCE on
@@ -130,6 +133,9 @@ int gbenv_get_counters(gbenv_t *h, gbenv_counters_t *out);
 /* Device time of the kernels launched by the last gbenv_step/gbenv_run_action call, measured with
  * CUDA events on the launching stream (ms).  which: 0 = emulate, 1 = obs/reward.  Synchronous.  */
 int gbenv_last_kernel_ms(gbenv_t *h, int which, float *ms_out);
+/* Running total of the same device times over every gbenv_step since create (CUDA events recorded on
+ * the launching stream around each kernel group; folding is lazy, so the step path never blocks).    */
+int gbenv_kernel_time_total(gbenv_t *h, int which, double *ms_total_out, uint64_t *steps_out);
 /* Non-serialised core fields (STATRegister._mode, Renderer.ly_window ...) for parity checks.    */
 typedef struct gbenv_core_extra {
     int32_t stat_mode;

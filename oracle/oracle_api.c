@@ -328,6 +328,19 @@ int oracle_last_kernel_ms(oracle *h, int which, float *ms) {
     return GBENV_OK;
 }
 
+int oracle_set_lanes_per_warp(oracle *h, int lanes) {
+    (void)lanes;
+    return h ? GBENV_OK : GBENV_E_ARG;
+}
+
+int oracle_kernel_time_total(oracle *h, int which, double *ms, uint64_t *steps) {
+    (void)h;
+    (void)which;
+    if (ms) *ms = 0.0;
+    if (steps) *steps = 0;
+    return GBENV_OK;
+}
+
 int oracle_get_core_extra(oracle *h, int env, gbenv_core_extra_t *out) {
     if (!h || env < 0 || env >= h->n || !out) return GBENV_E_ARG;
     out->stat_mode = h->envs[env].core.stat_mode;

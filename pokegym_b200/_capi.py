@@ -61,6 +61,7 @@ _SIGS = {
     "last_error": ([C.c_void_p], C.c_char_p),
     "num_envs": ([C.c_void_p], C.c_int),
     "sync": ([C.c_void_p], C.c_int),
+    "set_lanes_per_warp": ([C.c_void_p, C.c_int], C.c_int),
     "add_state_template": ([C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)], C.c_int),
     "load_template": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int], C.c_int),
     "set_initial_template": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int], C.c_int),
@@ -81,6 +82,7 @@ _SIGS = {
     "counts_map": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "get_counters": ([C.c_void_p, C.POINTER(Counters)], C.c_int),
     "last_kernel_ms": ([C.c_void_p, C.c_int, C.POINTER(C.c_float)], C.c_int),
+    "kernel_time_total": ([C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], C.c_int),
     "get_core_extra": ([C.c_void_p, C.c_int, C.POINTER(CoreExtra)], C.c_int),
 }
 
@@ -223,6 +225,9 @@ class Handle:
     def sync(self):
         self._check(self.lib.sync(self._h), "sync")
 
+    def set_lanes_per_warp(self, lanes: int):
+        self._check(self.lib.set_lanes_per_warp(self._h, int(lanes)), "set_lanes_per_warp")
+
     def counters(self) -> Counters:
         c = Counters()
         self._check(self.lib.get_counters(self._h, C.byref(c)), "get_counters")
@@ -232,6 +237,12 @@ class Handle:
         ms = C.c_float(0)
         self._check(self.lib.last_kernel_ms(self._h, int(which), C.byref(ms)), "last_kernel_ms")
         return ms.value
+
+    def kernel_time_total(self, which: int = 0):
+        """(total device ms, steps) of kernel group `which` (0 = emulate, 1 = reward + obs) since create."""
+        ms, steps = C.c_double(0), C.c_uint64(0)
+        self._check(self.lib.kernel_time_total(self._h, int(which), C.byref(ms), C.byref(steps)), "kernel_time_total")
+        return ms.value, steps.value
 
     def core_extra(self, env: int) -> CoreExtra:
         x = CoreExtra()

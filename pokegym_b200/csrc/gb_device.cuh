@@ -455,120 +455,129 @@ __device__ __forceinline__ int timer_cycles_to_interrupt(const Machine &m) {
 }
 
 // --------------------------------------------------------------------------------------------- bus
+// Two flavours of every bus function:
+//   *_full  : everything inline.  Used by the interpreter, which funnels ALL of an instruction's data
+//             accesses through one read site and one write site (cpu_step), so the big IO switch is
+//             instantiated once and `Machine` never has its address taken (it stays in registers).
+//   bus_read / bus_write : small inline fast path + out-of-line slow path, for the wrapper kernels and
+//             the debug bus access, where call-site count matters more than register residency.
 
-__device__ inline uint32_t bus_read(Machine &m, uint32_t a) {
+#define BUS_READ_BODY                                                                        \
+    if (a < 0xFF00) {                                                                        \
+        if (a >= 0xFE00) return mem_rd(m, MEM_HI + (a - 0xFE00));                            \
+        if (a >= 0xC000) return mem_rd(m, MEM_WRAM + (a & 0x1FFF)); /* WRAM + echo */       \
+        if (a >= 0xA000) {                                                                   \
+            if (!m.ram_en) return 0xFF;                                                      \
+            uint32_t i = (m.rambank & 3) * 0x2000u + (a - 0xA000);                           \
+            return m.cramb[((i >> 2) << 7) | (i & 3)];                                       \
+        }                                                                                    \
+        return mem_rd(m, MEM_VRAM + (a - 0x8000));                                           \
+    }                                                                                        \
+    if (a >= 0xFF80 && a < 0xFFFF) return mem_rd(m, MEM_HI + (a - 0xFE00)); /* HRAM */       \
+    switch (a) {                                                                             \
+    case 0xFF04: return m.div;                                                               \
+    case 0xFF05: return m.tima;                                                              \
+    case 0xFF06: return m.tma;                                                               \
+    case 0xFF07: return m.tac;                                                               \
+    case 0xFF0F: return m.iflag;                                                             \
+    case 0xFF40: return m.lcdc;                                                              \
+    case 0xFF41: return m.stat;                                                              \
+    case 0xFF42: return m.scy;                                                               \
+    case 0xFF43: return m.scx;                                                               \
+    case 0xFF44: return m.ly;                                                                \
+    case 0xFF45: return m.lyc;                                                               \
+    case 0xFF46: return 0;                                                                   \
+    case 0xFF47: return m.bgp;                                                               \
+    case 0xFF48: return m.obp0;                                                              \
+    case 0xFF49: return m.obp1;                                                              \
+    case 0xFF4A: return m.wy;                                                                \
+    case 0xFF4B: return m.wx;                                                                \
+    case 0xFFFF: return m.ie;                                                                \
+    default:                                                                                 \
+        if (a >= 0xFF10 && a < 0xFF40) return 0; /* sound disabled (pokegym default) */      \
+        return mem_rd(m, MEM_HI + (a - 0xFE00));                                             \
+    }
+
+__device__ __forceinline__ uint32_t bus_read_full(Machine &m, uint32_t a) {  // Motherboard.getitem
     if (a < 0x8000) return __ldg(m.rom + (a < 0x4000 ? a : a + m.rom_off));
-    if (a < 0xFF00) {
-        if (a >= 0xFE00) return mem_rd(m, MEM_HI + (a - 0xFE00));
-        if (a >= 0xC000) return mem_rd(m, MEM_WRAM + (a & 0x1FFF));  // WRAM and its echo
-        if (a >= 0xA000) {
-            if (!m.ram_en) return 0xFF;
-            uint32_t i = (m.rambank & 3) * 0x2000u + (a - 0xA000);
-            return m.cramb[((i >> 2) << 7) | (i & 3)];
-        }
-        return mem_rd(m, MEM_VRAM + (a - 0x8000));
-    }
-    switch (a) {
-    case 0xFF04: return m.div;
-    case 0xFF05: return m.tima;
-    case 0xFF06: return m.tma;
-    case 0xFF07: return m.tac;
-    case 0xFF0F: return m.iflag;
-    case 0xFF40: return m.lcdc;
-    case 0xFF41: return m.stat;
-    case 0xFF42: return m.scy;
-    case 0xFF43: return m.scx;
-    case 0xFF44: return m.ly;
-    case 0xFF45: return m.lyc;
-    case 0xFF46: return 0;
-    case 0xFF47: return m.bgp;
-    case 0xFF48: return m.obp0;
-    case 0xFF49: return m.obp1;
-    case 0xFF4A: return m.wy;
-    case 0xFF4B: return m.wx;
-    case 0xFFFF: return m.ie;
-    default:
-        if (a >= 0xFF10 && a < 0xFF40) return 0;  // sound disabled (pokegym default): reads 0
-        return mem_rd(m, MEM_HI + (a - 0xFE00));
-    }
+    BUS_READ_BODY
+}
+__device__ __noinline__ uint32_t bus_read_slow(Machine &m, uint32_t a) { BUS_READ_BODY }
+__device__ __forceinline__ uint32_t bus_read(Machine &m, uint32_t a) {
+    if (a < 0x8000) return __ldg(m.rom + (a < 0x4000 ? a : a + m.rom_off));
+    if (a >= 0xC000 && a < 0xE000) return mem_rd(m, MEM_WRAM + (a - 0xC000));
+    return bus_read_slow(m, a);
 }
 
-__device__ void bus_write(Machine &m, uint32_t a, uint32_t v);
-
-__device__ inline void oam_dma(Machine &m, uint32_t page) {
-    // Motherboard.transfer_DMA: instantaneous copy of 0xA0 bytes to OAM
+// Motherboard.transfer_DMA: instantaneous copy of 0xA0 bytes to OAM
+__device__ __forceinline__ void oam_dma(Machine &m, uint32_t page);
+__device__ __forceinline__ uint32_t bus_read_full(Machine &m, uint32_t a);
+__device__ __forceinline__ void oam_dma(Machine &m, uint32_t page) {
     uint32_t src = page << 8;
     bool plain = (page >= 0x80 && page < 0xA0) || (page >= 0xC0 && page < 0xFE);
     if (plain) {  // word copy inside the plain-RAM array (src is 256-byte aligned)
         uint32_t base = page < 0xA0 ? (MEM_VRAM + (src - 0x8000)) : (MEM_WRAM + (src & 0x1FFF));
         for (uint32_t k = 0; k < 40; k++) mem_wr_word(m, (MEM_HI >> 2) + k, mem_rd_word(m, (base >> 2) + k));
     } else {
-        for (uint32_t k = 0; k < 40; k++) {
-            uint32_t w = 0;
-            for (uint32_t b = 0; b < 4; b++) w |= bus_read(m, (src + k * 4 + b) & 0xFFFF) << (8 * b);
-            mem_wr_word(m, (MEM_HI >> 2) + k, w);
-        }
+        for (uint32_t k = 0; k < 160; k++) mem_wr(m, MEM_HI + k, bus_read_full(m, (src + k) & 0xFFFF));
     }
 }
 
-__device__ inline void bus_write(Machine &m, uint32_t a, uint32_t v) {
-    v &= 0xFF;
-    if (a >= 0xC000 && a < 0xFE00) {
-        mem_wr(m, MEM_WRAM + (a & 0x1FFF), v);
-        return;
+#define BUS_WRITE_BODY                                                                                    \
+    v &= 0xFF;                                                                                            \
+    if (a >= 0xC000 && a < 0xFE00) { mem_wr(m, MEM_WRAM + (a & 0x1FFF), v); return; }                     \
+    if (a < 0x8000) { /* MBC3 registers */                                                                \
+        if (a < 0x2000) {                                                                                 \
+            if ((v & 0x0F) == 0x0A) m.ram_en = 1;                                                         \
+            else if (v == 0) m.ram_en = 0; /* PyBoy: any other value leaves the latch untouched */        \
+        } else if (a < 0x4000) {                                                                          \
+            v &= 0x7F;                                                                                    \
+            machine_set_rombank(m, v ? v : 1);                                                            \
+        } else if (a < 0x6000) {                                                                          \
+            m.rambank = v;                                                                                \
+        }                                                                                                 \
+        return;                                                                                           \
+    }                                                                                                     \
+    if (a < 0xA000) { mem_wr(m, MEM_VRAM + (a - 0x8000), v); return; }                                    \
+    if (a < 0xC000) {                                                                                     \
+        if (m.ram_en && m.rambank <= 3) {                                                                 \
+            uint32_t i = m.rambank * 0x2000u + (a - 0xA000);                                              \
+            m.cramb[((i >> 2) << 7) | (i & 3)] = (uint8_t)v;                                              \
+        }                                                                                                 \
+        return;                                                                                           \
+    }                                                                                                     \
+    if (a < 0xFF00 || (a >= 0xFF80 && a < 0xFFFF)) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }       \
+    switch (a) {                                                                                          \
+    case 0xFF00: mem_wr(m, MEM_HI + 0x100, joypad_pull(m, v)); break;                                     \
+    case 0xFF04: m.div = 0; m.divc = 0; m.timac = 0; break;                                               \
+    case 0xFF05: m.tima = v; break;                                                                       \
+    case 0xFF06: m.tma = v; break;                                                                        \
+    case 0xFF07: m.tac = v & 7; break;                                                                    \
+    case 0xFF0F: m.iflag = v; break;                                                                      \
+    case 0xFF40: lcd_set_lcdc(m, v); break;                                                               \
+    case 0xFF41: m.stat = (m.stat & 0x87) | (v & 0x78); break;                                            \
+    case 0xFF42: if (v != m.scy) m.lp_dirty = 144; m.scy = v; break;                                      \
+    case 0xFF43: if (v != m.scx) m.lp_dirty = 144; m.scx = v; break;                                      \
+    case 0xFF44: m.ly = v; m.lp_dirty = 144; break; /* PyBoy lets LY be written */                        \
+    case 0xFF45: m.lyc = v; break;                                                                        \
+    case 0xFF46: oam_dma(m, v); break;                                                                    \
+    case 0xFF47: m.bgp = v; break;                                                                        \
+    case 0xFF48: m.obp0 = v; break;                                                                       \
+    case 0xFF49: m.obp1 = v; break;                                                                       \
+    case 0xFF4A: if (v != m.wy) m.lp_dirty = 144; m.wy = v; break;                                        \
+    case 0xFF4B: if (v != m.wx) m.lp_dirty = 144; m.wx = v; break;                                        \
+    case 0xFFFF: m.ie = v; break;                                                                         \
+    default:                                                                                              \
+        if (a >= 0xFF10 && a < 0xFF40) break; /* sound disabled: writes dropped */                        \
+        mem_wr(m, MEM_HI + (a - 0xFE00), v);                                                              \
+        break;                                                                                            \
     }
-    if (a < 0x8000) {  // MBC3 registers
-        if (a < 0x2000) {
-            if ((v & 0x0F) == 0x0A) m.ram_en = 1;
-            else if (v == 0) m.ram_en = 0;  // PyBoy: any other value leaves the latch untouched
-        } else if (a < 0x4000) {
-            v &= 0x7F;
-            machine_set_rombank(m, v ? v : 1);
-        } else if (a < 0x6000) {
-            m.rambank = v;
-        }
-        return;
-    }
-    if (a < 0xA000) {
-        mem_wr(m, MEM_VRAM + (a - 0x8000), v);
-        return;
-    }
-    if (a < 0xC000) {
-        if (m.ram_en && m.rambank <= 3) {
-            uint32_t i = m.rambank * 0x2000u + (a - 0xA000);
-            m.cramb[((i >> 2) << 7) | (i & 3)] = (uint8_t)v;
-        }
-        return;
-    }
-    if (a < 0xFF00) {
-        mem_wr(m, MEM_HI + (a - 0xFE00), v);
-        return;
-    }
-    switch (a) {
-    case 0xFF00: mem_wr(m, MEM_HI + 0x100, joypad_pull(m, v)); break;
-    case 0xFF04: m.div = 0; m.divc = 0; m.timac = 0; break;
-    case 0xFF05: m.tima = v; break;
-    case 0xFF06: m.tma = v; break;
-    case 0xFF07: m.tac = v & 7; break;
-    case 0xFF0F: m.iflag = v; break;
-    case 0xFF40: lcd_set_lcdc(m, v); break;
-    case 0xFF41: m.stat = (m.stat & 0x87) | (v & 0x78); break;
-    case 0xFF42: if (v != m.scy) m.lp_dirty = 144; m.scy = v; break;
-    case 0xFF43: if (v != m.scx) m.lp_dirty = 144; m.scx = v; break;
-    case 0xFF44: m.ly = v; m.lp_dirty = 144; break;  // PyBoy lets LY be written
-    case 0xFF45: m.lyc = v; break;
-    case 0xFF46: oam_dma(m, v); break;
-    case 0xFF47: m.bgp = v; break;
-    case 0xFF48: m.obp0 = v; break;
-    case 0xFF49: m.obp1 = v; break;
-    case 0xFF4A: if (v != m.wy) m.lp_dirty = 144; m.wy = v; break;
-    case 0xFF4B: if (v != m.wx) m.lp_dirty = 144; m.wx = v; break;
-    case 0xFFFF: m.ie = v; break;
-    default:
-        if (a >= 0xFF10 && a < 0xFF40) break;  // sound disabled: writes dropped
-        mem_wr(m, MEM_HI + (a - 0xFE00), v);
-        break;
-    }
+
+__device__ __forceinline__ void bus_write_full(Machine &m, uint32_t a, uint32_t v) { BUS_WRITE_BODY }  // Motherboard.setitem
+__device__ __noinline__ void bus_write_slow(Machine &m, uint32_t a, uint32_t v) { BUS_WRITE_BODY }
+__device__ __forceinline__ void bus_write(Machine &m, uint32_t a, uint32_t v) {
+    if (a >= 0xC000 && a < 0xE000) mem_wr(m, MEM_WRAM + (a - 0xC000), v);
+    else bus_write_slow(m, a, v);
 }
 
 // ------------------------------------------------------------------------------------------- SM83
@@ -604,16 +613,6 @@ __device__ __forceinline__ bool condition(const Machine &m, uint32_t cc) {  // N
     uint32_t bit = (cc & 2) ? (f & FLAG_C) : (f & FLAG_Z);
     return (bit != 0) == ((cc & 1) != 0);
 }
-__device__ __forceinline__ void push16(Machine &m, uint32_t v) {
-    bus_write(m, (m.sp - 1) & 0xFFFF, v >> 8);
-    bus_write(m, (m.sp - 2) & 0xFFFF, v & 0xFF);
-    m.sp = (m.sp - 2) & 0xFFFF;
-}
-__device__ __forceinline__ uint32_t pop16(Machine &m) {
-    uint32_t lo = bus_read(m, m.sp), hi = bus_read(m, (m.sp + 1) & 0xFFFF);
-    m.sp = (m.sp + 2) & 0xFFFF;
-    return lo | (hi << 8);
-}
 
 // 8-bit ALU group (ADD ADC SUB SBC AND XOR OR CP) on A with operand v
 __device__ __forceinline__ void alu8(Machine &m, uint32_t op, uint32_t v) {
@@ -638,284 +637,320 @@ __device__ __forceinline__ void alu8(Machine &m, uint32_t op, uint32_t v) {
     set_af(m, res, nf);
 }
 
-// CB-prefixed page; returns cycles
-__device__ inline uint32_t exec_cb(Machine &m) {
-    uint32_t op = bus_read(m, (m.pc + 1) & 0xFFFF);
-    m.pc = (m.pc + 2) & 0xFFFF;
-    uint32_t r = op & 7, y = (op >> 3) & 7, x = op >> 6;
-    uint32_t v = (r == 6) ? bus_read(m, reg_hl(m)) : reg8(m, r);
-    uint32_t f = reg_f(m), res;
-    if (x == 1) {  // BIT: Z from the tested bit, H set, C kept
-        set_f(m, (f & FLAG_C) | FLAG_H | (((v >> y) & 1) ? 0 : FLAG_Z));
-        return r == 6 ? 16 : 8;  // PyBoy's table charges 16 for BIT b,(HL)
+// Instruction fetch: opcode plus its two possible operand bytes as one little-endian word.  Code almost
+// always runs from cartridge ROM, where the three bytes come from two aligned 32-bit read-only loads
+// (the ROM image is padded, so the second load is always in bounds); RAM code takes the byte path.
+__device__ __forceinline__ uint32_t fetch3(Machine &m, uint32_t pc) {
+    if (pc < 0x7FFD && (pc & 0x3FFF) < 0x3FFD) {  // the whole instruction lies inside one ROM bank window
+        uint32_t addr = pc < 0x4000 ? pc : pc + m.rom_off;
+        const uint32_t *w = (const uint32_t *)(m.rom + (addr & ~3u));
+        return __funnelshift_r(__ldg(w), __ldg(w + 1), (addr & 3) * 8);
     }
-    if (x == 0) {
-        uint32_t c = (f >> 4) & 1, cout;
-        switch (y) {
-        case 0: cout = v >> 7; res = (v << 1) | cout; break;           // RLC
-        case 1: cout = v & 1; res = (v >> 1) | (cout << 7); break;     // RRC
-        case 2: cout = v >> 7; res = (v << 1) | c; break;              // RL
-        case 3: cout = v & 1; res = (v >> 1) | (c << 7); break;        // RR
-        case 4: cout = v >> 7; res = v << 1; break;                    // SLA
-        case 5: cout = v & 1; res = (v >> 1) | (v & 0x80); break;      // SRA
-        case 6: cout = 0; res = (v >> 4) | (v << 4); break;            // SWAP
-        default: cout = v & 1; res = v >> 1; break;                    // SRL
-        }
-        res &= 0xFF;
-        set_f(m, (res == 0 ? FLAG_Z : 0) | (cout ? FLAG_C : 0));
-    } else {
-        res = (x == 2) ? (v & ~(1u << y)) : (v | (1u << y));  // RES / SET
-    }
-    if (r == 6) bus_write(m, reg_hl(m), res);
-    else set_reg8(m, r, res);
-    return r == 6 ? 16 : 8;
+    uint32_t ins = 0;
+    for (uint32_t i = 0; i < 3; i++) ins |= bus_read_full(m, (pc + i) & 0xFFFF) << (8 * i);
+    return ins;
 }
 
-// fetch + execute one instruction; returns T-cycles (pastraiser table as used by PyBoy)
-__device__ inline uint32_t exec_instruction(Machine &m) {
-    const uint32_t pc = m.pc;
-    const uint32_t op = bus_read(m, pc);
-    const uint32_t x = op >> 6, y = (op >> 3) & 7, z = op & 7, p = y >> 1, q = y & 1;
-#define IMM8() bus_read(m, (pc + 1) & 0xFFFF)
-#define IMM16() (bus_read(m, (pc + 1) & 0xFFFF) | (bus_read(m, (pc + 2) & 0xFFFF) << 8))
-#define NEXT(n) m.pc = (pc + (n)) & 0xFFFF
+// CPU.tick: interrupt check, HALT handling, one instruction.  Returns T-cycles (pastraiser table as used
+// by PyBoy; interrupt dispatch costs 0).  Every data access of the instruction goes through ONE read
+// site (up to two consecutive bytes: operand or 16-bit pop) and ONE write site (up to two bytes: operand,
+// 16-bit push or LD (nn),SP), so threads executing different opcodes still share the memory code.
+__device__ __forceinline__ uint32_t cpu_step(Machine &m) {
+    uint32_t wn = 0, w0a = 0, w0v = 0, w1a = 0, w1v = 0;  // deferred bus writes, issued in order w0, w1
+    uint32_t cycles = 0;
+#define PUSH16(val)                                  \
+    do {                                             \
+        uint32_t _v = (val);                         \
+        w0a = (m.sp - 1) & 0xFFFF; w0v = _v >> 8;    \
+        w1a = (m.sp - 2) & 0xFFFF; w1v = _v & 0xFF;  \
+        wn = 2;                                      \
+        m.sp = (m.sp - 2) & 0xFFFF;                  \
+    } while (0)
+#define WRITE8(addr, val) do { w0a = (addr) & 0xFFFF; w0v = (val); wn = 1; } while (0)
 
-    if (x == 1) {
-        if (op == 0x76) {  // HALT: PC stays on the HALT byte, wake-up adds 1
-            m.halted = 1;
-            return 4;
-        }
-        uint32_t v = (z == 6) ? bus_read(m, reg_hl(m)) : reg8(m, z);
-        if (y == 6) bus_write(m, reg_hl(m), v);
-        else set_reg8(m, y, v);
-        NEXT(1);
-        return (y == 6 || z == 6) ? 8 : 4;
-    }
-    if (x == 2) {
-        alu8(m, y, (z == 6) ? bus_read(m, reg_hl(m)) : reg8(m, z));
-        NEXT(1);
-        return z == 6 ? 8 : 4;
-    }
-    if (x == 0) {
-        switch (z) {
-        case 0:
-            if (y == 0) { NEXT(1); return 4; }
-            if (y == 1) {  // LD (nn),SP
-                uint32_t a = IMM16();
-                bus_write(m, a, m.sp & 0xFF);
-                bus_write(m, (a + 1) & 0xFFFF, m.sp >> 8);
-                NEXT(3);
-                return 20;
-            }
-            if (y == 2) { NEXT(2); return 4; }  // STOP
-            if (y == 3 || condition(m, y - 4)) {  // JR
-                uint32_t e = IMM8();
-                m.pc = (pc + 2 + ((e ^ 0x80) - 0x80)) & 0xFFFF;
-                return 12;
-            }
-            NEXT(2);
-            return 8;
-        case 1:
-            if (q == 0) {
-                set_reg_pair(m, p, IMM16());
-                NEXT(3);
-                return 12;
-            } else {  // ADD HL,rp
-                uint32_t hl = reg_hl(m), v = reg_pair(m, p), t = hl + v;
-                set_f(m, (reg_f(m) & FLAG_Z) | (((hl & 0xFFF) + (v & 0xFFF)) > 0xFFF ? FLAG_H : 0) | (t > 0xFFFF ? FLAG_C : 0));
-                set_hl(m, t);
-                NEXT(1);
-                return 8;
-            }
-        case 2: {
-            uint32_t a = (p == 0) ? (m.bcde & 0xFFFF) : (p == 1) ? (m.bcde >> 16) : reg_hl(m);
-            if (q == 0) bus_write(m, a, reg_a(m));
-            else set_a(m, bus_read(m, a));
-            if (p == 2) set_hl(m, a + 1);
-            else if (p == 3) set_hl(m, a - 1);
-            NEXT(1);
-            return 8;
-        }
-        case 3:
-            set_reg_pair(m, p, reg_pair(m, p) + (q ? 0xFFFFu : 1u));
-            NEXT(1);
-            return 8;
-        case 4:
-        case 5: {  // INC r / DEC r
-            uint32_t v = (y == 6) ? bus_read(m, reg_hl(m)) : reg8(m, y), res, nf = reg_f(m) & FLAG_C;
-            if (z == 4) {
-                res = (v + 1) & 0xFF;
-                nf |= ((v & 0xF) == 0xF ? FLAG_H : 0);
-            } else {
-                res = (v - 1) & 0xFF;
-                nf |= FLAG_N | ((v & 0xF) == 0 ? FLAG_H : 0);
-            }
-            if (res == 0) nf |= FLAG_Z;
-            set_f(m, nf);
-            if (y == 6) bus_write(m, reg_hl(m), res);
-            else set_reg8(m, y, res);
-            NEXT(1);
-            return y == 6 ? 12 : 4;
-        }
-        case 6: {
-            uint32_t v = IMM8();
-            if (y == 6) bus_write(m, reg_hl(m), v);
-            else set_reg8(m, y, v);
-            NEXT(2);
-            return y == 6 ? 12 : 8;
-        }
-        default: {
-            uint32_t a = reg_a(m), f = reg_f(m), c = (f >> 4) & 1;
-            switch (y) {
-            case 0: set_af(m, (a << 1) | (a >> 7), (a >> 7) ? FLAG_C : 0); break;         // RLCA
-            case 1: set_af(m, (a >> 1) | (a << 7), (a & 1) ? FLAG_C : 0); break;          // RRCA
-            case 2: set_af(m, (a << 1) | c, (a >> 7) ? FLAG_C : 0); break;                // RLA
-            case 3: set_af(m, (a >> 1) | (c << 7), (a & 1) ? FLAG_C : 0); break;          // RRA
-            case 4: {                                                                     // DAA
-                uint32_t corr = ((f & FLAG_H) ? 0x06 : 0) | ((f & FLAG_C) ? 0x60 : 0), t = a;
-                if (f & FLAG_N) {
-                    t -= corr;
-                } else {
-                    if ((t & 0x0F) > 9) corr |= 0x06;
-                    if (t > 0x99) corr |= 0x60;
-                    t += corr;
-                }
-                t &= 0xFF;
-                set_af(m, t, (f & FLAG_N) | (t == 0 ? FLAG_Z : 0) | ((corr & 0x60) ? FLAG_C : 0));
-                break;
-            }
-            case 5: set_af(m, ~a, f | FLAG_N | FLAG_H); break;                            // CPL
-            case 6: set_f(m, (f & FLAG_Z) | FLAG_C); break;                               // SCF
-            default: set_f(m, (f & FLAG_Z) | ((f & FLAG_C) ^ FLAG_C)); break;             // CCF
-            }
-            NEXT(1);
-            return 4;
-        }
-        }
-    }
-    // x == 3
-    switch (z) {
-    case 0:
-        if (y < 4) {  // RET cc
-            if (condition(m, y)) { m.pc = pop16(m); return 20; }
-            NEXT(1);
-            return 8;
-        }
-        if (y == 4) { bus_write(m, 0xFF00 + IMM8(), reg_a(m)); NEXT(2); return 12; }
-        if (y == 6) { set_a(m, bus_read(m, 0xFF00 + IMM8())); NEXT(2); return 12; }
-        {  // ADD SP,e / LD HL,SP+e
-            uint32_t e = IMM8(), sp = m.sp;
-            uint32_t nf = (((sp & 0xF) + (e & 0xF)) > 0xF ? FLAG_H : 0) | (((sp & 0xFF) + e) > 0xFF ? FLAG_C : 0);
-            uint32_t t = (sp + ((e ^ 0x80) - 0x80)) & 0xFFFF;
-            set_f(m, nf);
-            NEXT(2);
-            if (y == 5) { m.sp = t; return 16; }
-            set_hl(m, t);
-            return 12;
-        }
-    case 1:
-        if (q == 0) {  // POP
-            uint32_t v = pop16(m);
-            if (p == 3) set_af(m, v >> 8, v & 0xF0);
-            else set_reg_pair(m, p, v);
-            NEXT(1);
-            return 12;
-        }
-        if (p == 0) { m.pc = pop16(m); return 16; }
-        if (p == 1) { m.ime = 1; m.pc = pop16(m); return 16; }
-        if (p == 2) { m.pc = reg_hl(m); return 4; }
-        m.sp = reg_hl(m);
-        NEXT(1);
-        return 8;
-    case 2:
-        if (y < 4) {
-            if (condition(m, y)) { m.pc = IMM16(); return 16; }
-            NEXT(3);
-            return 12;
-        }
-        if (y == 4) { bus_write(m, 0xFF00 + (m.bcde & 0xFF), reg_a(m)); NEXT(1); return 8; }
-        if (y == 5) { bus_write(m, IMM16(), reg_a(m)); NEXT(3); return 16; }
-        if (y == 6) { set_a(m, bus_read(m, 0xFF00 + (m.bcde & 0xFF))); NEXT(1); return 8; }
-        set_a(m, bus_read(m, IMM16()));
-        NEXT(3);
-        return 16;
-    case 3:
-        if (y == 0) { m.pc = IMM16(); return 16; }
-        if (y == 1) return exec_cb(m);
-        if (y == 6) { m.ime = 0; NEXT(1); return 4; }
-        if (y == 7) { m.ime = 1; NEXT(1); return 4; }  // PyBoy: EI takes effect immediately
-        break;
-    case 4:
-        if (y < 4) {
-            NEXT(3);
-            if (condition(m, y)) {
-                uint32_t t = IMM16();
-                push16(m, m.pc);
-                m.pc = t;
-                return 24;
-            }
-            return 12;
-        }
-        break;
-    case 5:
-        if (q == 0) {  // PUSH
-            uint32_t v = (p == 3) ? ((reg_a(m) << 8) | reg_f(m)) : reg_pair(m, p);
-            push16(m, v);
-            NEXT(1);
-            return 16;
-        }
-        if (p == 0) {  // CALL nn
-            uint32_t t = IMM16();
-            NEXT(3);
-            push16(m, m.pc);
-            m.pc = t;
-            return 24;
-        }
-        break;
-    case 6:
-        alu8(m, y, IMM8());
-        NEXT(2);
-        return 8;
-    default:  // RST
-        NEXT(1);
-        push16(m, m.pc);
-        m.pc = y * 8;
-        return 16;
-    }
-    // illegal opcode (PyBoy raises): latch a fault, behave as a 1-byte 4-cycle NOP
-    m.fault = 1;
-    NEXT(1);
-    return 4;
-#undef IMM8
-#undef IMM16
-#undef NEXT
-}
-
-// CPU.tick: interrupt check, HALT handling, one instruction.  Returns cycles.
-__device__ __forceinline__ uint32_t cpu_tick(Machine &m) {
+    bool execute = true;
     if (!m.iq) {
         uint32_t pending = m.iflag & m.ie & 0x1F;
-        if (pending) {
-            // CPU.handle_interrupt for the highest-priority pending source
+        if (pending) {  // CPU.handle_interrupt for the highest-priority pending source
             uint32_t bit = pending & (0u - pending);
             if (m.halted) m.pc = (m.pc + 1) & 0xFFFF;
             if (m.ime) {
                 m.iflag ^= bit;
-                push16(m, m.pc);
+                PUSH16(m.pc);
                 m.pc = 0x40 + 8 * (31 - __clz(bit));
                 m.ime = 0;
             }
             m.iq = 1;
             m.halted = 0;
-            return 0;  // PyBoy charges no cycles for the dispatch
+            execute = false;  // PyBoy charges no cycles for the dispatch
         }
-    } else if (m.halted) {
-        m.halted = 0;  // debugger-only path in PyBoy: halted with a queued interrupt
+    } else if (m.halted) {  // debugger-only path in PyBoy: halted with a queued interrupt
+        m.halted = 0;
         m.pc = (m.pc + 1) & 0xFFFF;
     }
-    if (m.halted) return 4;
-    uint32_t c = exec_instruction(m);
-    m.n_instr++;
-    m.iq = 0;
-    return c;
+    if (execute && m.halted) return 4;
+    if (execute) {
+        const uint32_t pc = m.pc;
+        const uint32_t ins = fetch3(m, pc);
+        const uint32_t op = ins & 0xFF, imm8 = (ins >> 8) & 0xFF, imm16 = (ins >> 8) & 0xFFFF;
+        const bool cb = op == 0xCB;
+        const uint32_t dop = cb ? imm8 : op;  // the byte whose x/y/z fields select the operation
+        const uint32_t x = dop >> 6, y = (dop >> 3) & 7, z = dop & 7, p = y >> 1, q = y & 1;
+        const uint32_t hl = reg_hl(m);
+        // ---- read phase: which bytes does this instruction load?
+        uint32_t rn = 0, ra = hl;
+        if (cb) {
+            rn = z == 6;
+        } else if (x == 0) {
+            if ((z == 4 || z == 5) && y == 6) rn = 1;
+            else if (z == 2 && q == 1) { rn = 1; ra = p == 0 ? (m.bcde & 0xFFFF) : p == 1 ? (m.bcde >> 16) : hl; }
+        } else if (x == 1 || x == 2) {
+            rn = (z == 6 && op != 0x76);
+        } else {
+            if (z == 0) {
+                if (y < 4) { if (condition(m, y)) { rn = 2; ra = m.sp; } }
+                else if (y == 6) { rn = 1; ra = 0xFF00 + imm8; }
+            } else if (z == 1) {
+                if (q == 0 || p < 2) { rn = 2; ra = m.sp; }
+            } else if (z == 2) {
+                if (y == 6) { rn = 1; ra = 0xFF00 + (m.bcde & 0xFF); }
+                else if (y == 7) { rn = 1; ra = imm16; }
+            }
+        }
+        uint32_t rv = 0;
+        for (uint32_t i = 0; i < rn; i++) rv |= bus_read_full(m, (ra + i) & 0xFFFF) << (8 * i);
+        // ---- execute phase (registers only)
+#define NEXT(n) m.pc = (pc + (n)) & 0xFFFF
+        if (cb) {
+            NEXT(2);
+            uint32_t v = (z == 6) ? rv : reg8(m, z), f = reg_f(m), res;
+            cycles = z == 6 ? 16 : 8;  // PyBoy's table charges 16 for BIT b,(HL) as well
+            if (x == 1) {  // BIT: Z from the tested bit, H set, C kept
+                set_f(m, (f & FLAG_C) | FLAG_H | (((v >> y) & 1) ? 0 : FLAG_Z));
+            } else {
+                if (x == 0) {
+                    uint32_t c = (f >> 4) & 1, cout;
+                    switch (y) {
+                    case 0: cout = v >> 7; res = (v << 1) | cout; break;        // RLC
+                    case 1: cout = v & 1; res = (v >> 1) | (cout << 7); break;  // RRC
+                    case 2: cout = v >> 7; res = (v << 1) | c; break;           // RL
+                    case 3: cout = v & 1; res = (v >> 1) | (c << 7); break;     // RR
+                    case 4: cout = v >> 7; res = v << 1; break;                 // SLA
+                    case 5: cout = v & 1; res = (v >> 1) | (v & 0x80); break;   // SRA
+                    case 6: cout = 0; res = (v >> 4) | (v << 4); break;         // SWAP
+                    default: cout = v & 1; res = v >> 1; break;                 // SRL
+                    }
+                    res &= 0xFF;
+                    set_f(m, (res == 0 ? FLAG_Z : 0) | (cout ? FLAG_C : 0));
+                } else {
+                    res = (x == 2) ? (v & ~(1u << y)) : (v | (1u << y));  // RES / SET
+                }
+                if (z == 6) WRITE8(hl, res);
+                else set_reg8(m, z, res);
+            }
+        } else if (x == 1) {
+            if (op == 0x76) {  // HALT: PC stays on the HALT byte, wake-up adds 1
+                m.halted = 1;
+                cycles = 4;
+            } else {
+                uint32_t v = (z == 6) ? rv : reg8(m, z);
+                if (y == 6) WRITE8(hl, v);
+                else set_reg8(m, y, v);
+                NEXT(1);
+                cycles = (y == 6 || z == 6) ? 8 : 4;
+            }
+        } else if (x == 2) {
+            alu8(m, y, (z == 6) ? rv : reg8(m, z));
+            NEXT(1);
+            cycles = z == 6 ? 8 : 4;
+        } else if (x == 0) {
+            switch (z) {
+            case 0:
+                if (y == 0) { NEXT(1); cycles = 4; }
+                else if (y == 1) {  // LD (nn),SP: low byte first
+                    w0a = imm16; w0v = m.sp & 0xFF; w1a = (imm16 + 1) & 0xFFFF; w1v = m.sp >> 8; wn = 2;
+                    NEXT(3);
+                    cycles = 20;
+                } else if (y == 2) { NEXT(2); cycles = 4; }  // STOP
+                else if (y == 3 || condition(m, y - 4)) {  // JR
+                    m.pc = (pc + 2 + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;
+                    cycles = 12;
+                } else { NEXT(2); cycles = 8; }
+                break;
+            case 1:
+                if (q == 0) {
+                    set_reg_pair(m, p, imm16);
+                    NEXT(3);
+                    cycles = 12;
+                } else {  // ADD HL,rp
+                    uint32_t v = reg_pair(m, p), t = hl + v;
+                    set_f(m, (reg_f(m) & FLAG_Z) | (((hl & 0xFFF) + (v & 0xFFF)) > 0xFFF ? FLAG_H : 0) | (t > 0xFFFF ? FLAG_C : 0));
+                    set_hl(m, t);
+                    NEXT(1);
+                    cycles = 8;
+                }
+                break;
+            case 2: {
+                uint32_t a = (p == 0) ? (m.bcde & 0xFFFF) : (p == 1) ? (m.bcde >> 16) : hl;
+                if (q == 0) WRITE8(a, reg_a(m));
+                else set_a(m, rv);
+                if (p == 2) set_hl(m, a + 1);
+                else if (p == 3) set_hl(m, a - 1);
+                NEXT(1);
+                cycles = 8;
+                break;
+            }
+            case 3:
+                set_reg_pair(m, p, reg_pair(m, p) + (q ? 0xFFFFu : 1u));
+                NEXT(1);
+                cycles = 8;
+                break;
+            case 4:
+            case 5: {  // INC r / DEC r
+                uint32_t v = (y == 6) ? rv : reg8(m, y), res, nf = reg_f(m) & FLAG_C;
+                if (z == 4) {
+                    res = (v + 1) & 0xFF;
+                    nf |= ((v & 0xF) == 0xF ? FLAG_H : 0);
+                } else {
+                    res = (v - 1) & 0xFF;
+                    nf |= FLAG_N | ((v & 0xF) == 0 ? FLAG_H : 0);
+                }
+                if (res == 0) nf |= FLAG_Z;
+                set_f(m, nf);
+                if (y == 6) WRITE8(hl, res);
+                else set_reg8(m, y, res);
+                NEXT(1);
+                cycles = y == 6 ? 12 : 4;
+                break;
+            }
+            case 6:
+                if (y == 6) WRITE8(hl, imm8);
+                else set_reg8(m, y, imm8);
+                NEXT(2);
+                cycles = y == 6 ? 12 : 8;
+                break;
+            default: {
+                uint32_t a = reg_a(m), f = reg_f(m), c = (f >> 4) & 1;
+                switch (y) {
+                case 0: set_af(m, (a << 1) | (a >> 7), (a >> 7) ? FLAG_C : 0); break;  // RLCA
+                case 1: set_af(m, (a >> 1) | (a << 7), (a & 1) ? FLAG_C : 0); break;   // RRCA
+                case 2: set_af(m, (a << 1) | c, (a >> 7) ? FLAG_C : 0); break;         // RLA
+                case 3: set_af(m, (a >> 1) | (c << 7), (a & 1) ? FLAG_C : 0); break;   // RRA
+                case 4: {                                                              // DAA
+                    uint32_t corr = ((f & FLAG_H) ? 0x06 : 0) | ((f & FLAG_C) ? 0x60 : 0), t = a;
+                    if (f & FLAG_N) {
+                        t -= corr;
+                    } else {
+                        if ((t & 0x0F) > 9) corr |= 0x06;
+                        if (t > 0x99) corr |= 0x60;
+                        t += corr;
+                    }
+                    t &= 0xFF;
+                    set_af(m, t, (f & FLAG_N) | (t == 0 ? FLAG_Z : 0) | ((corr & 0x60) ? FLAG_C : 0));
+                    break;
+                }
+                case 5: set_af(m, ~a, f | FLAG_N | FLAG_H); break;                     // CPL
+                case 6: set_f(m, (f & FLAG_Z) | FLAG_C); break;                        // SCF
+                default: set_f(m, (f & FLAG_Z) | ((f & FLAG_C) ^ FLAG_C)); break;      // CCF
+                }
+                NEXT(1);
+                cycles = 4;
+                break;
+            }
+            }
+        } else {  // x == 3
+            bool illegal = false;
+            switch (z) {
+            case 0:
+                if (y < 4) {  // RET cc
+                    if (rn) { m.pc = rv; m.sp = (m.sp + 2) & 0xFFFF; cycles = 20; }
+                    else { NEXT(1); cycles = 8; }
+                } else if (y == 4) { WRITE8(0xFF00 + imm8, reg_a(m)); NEXT(2); cycles = 12; }
+                else if (y == 6) { set_a(m, rv); NEXT(2); cycles = 12; }
+                else {  // ADD SP,e / LD HL,SP+e
+                    uint32_t sp = m.sp;
+                    uint32_t nf = (((sp & 0xF) + (imm8 & 0xF)) > 0xF ? FLAG_H : 0) | (((sp & 0xFF) + imm8) > 0xFF ? FLAG_C : 0);
+                    uint32_t t = (sp + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;
+                    set_f(m, nf);
+                    NEXT(2);
+                    if (y == 5) { m.sp = t; cycles = 16; }
+                    else { set_hl(m, t); cycles = 12; }
+                }
+                break;
+            case 1:
+                if (q == 0) {  // POP
+                    m.sp = (m.sp + 2) & 0xFFFF;
+                    if (p == 3) set_af(m, rv >> 8, rv & 0xF0);
+                    else set_reg_pair(m, p, rv);
+                    NEXT(1);
+                    cycles = 12;
+                } else if (p < 2) {  // RET / RETI
+                    if (p == 1) m.ime = 1;
+                    m.pc = rv;
+                    m.sp = (m.sp + 2) & 0xFFFF;
+                    cycles = 16;
+                } else if (p == 2) { m.pc = hl; cycles = 4; }
+                else { m.sp = hl; NEXT(1); cycles = 8; }
+                break;
+            case 2:
+                if (y < 4) {
+                    if (condition(m, y)) { m.pc = imm16; cycles = 16; }
+                    else { NEXT(3); cycles = 12; }
+                } else if (y == 4) { WRITE8(0xFF00 + (m.bcde & 0xFF), reg_a(m)); NEXT(1); cycles = 8; }
+                else if (y == 5) { WRITE8(imm16, reg_a(m)); NEXT(3); cycles = 16; }
+                else if (y == 6) { set_a(m, rv); NEXT(1); cycles = 8; }
+                else { set_a(m, rv); NEXT(3); cycles = 16; }
+                break;
+            case 3:
+                if (y == 0) { m.pc = imm16; cycles = 16; }
+                else if (y == 6) { m.ime = 0; NEXT(1); cycles = 4; }
+                else if (y == 7) { m.ime = 1; NEXT(1); cycles = 4; }  // PyBoy: EI takes effect immediately
+                else illegal = true;  // (y == 1 is the CB prefix, handled above)
+                break;
+            case 4:
+                if (y < 4) {
+                    NEXT(3);
+                    if (condition(m, y)) { PUSH16(m.pc); m.pc = imm16; cycles = 24; }
+                    else cycles = 12;
+                } else illegal = true;
+                break;
+            case 5:
+                if (q == 0) {  // PUSH
+                    PUSH16((p == 3) ? ((reg_a(m) << 8) | reg_f(m)) : reg_pair(m, p));
+                    NEXT(1);
+                    cycles = 16;
+                } else if (p == 0) {  // CALL nn
+                    NEXT(3);
+                    PUSH16(m.pc);
+                    m.pc = imm16;
+                    cycles = 24;
+                } else illegal = true;
+                break;
+            case 6:
+                alu8(m, y, imm8);
+                NEXT(2);
+                cycles = 8;
+                break;
+            default:  // RST
+                NEXT(1);
+                PUSH16(m.pc);
+                m.pc = y * 8;
+                cycles = 16;
+                break;
+            }
+            if (illegal) {  // PyBoy raises; we latch a fault and behave as a 1-byte 4-cycle NOP
+                m.fault = 1;
+                NEXT(1);
+                cycles = 4;
+            }
+        }
+#undef NEXT
+        m.n_instr++;
+        m.iq = 0;
+    }
+    // ---- write phase
+    for (uint32_t i = 0; i < wn; i++) bus_write_full(m, i ? w1a : w0a, i ? w1v : w0v);
+#undef PUSH16
+#undef WRITE8
+    return cycles;
 }

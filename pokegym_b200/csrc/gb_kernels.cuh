@@ -14,6 +14,7 @@ struct RunParams {
     int n_frames;
     int render_mode;  // 0: renderer disabled, 1: enabled on every frame, 2: enabled on the last frame only
     int release_frame;  // frame index at which the button is released (8 in the reference)
+    int lanes;          // envs per warp (1..32, power of two): fewer lanes = more warps = more latency hiding
     unsigned long long *counters;  // [0] instructions, [1] cycles, [2] frames, [3] faults
 };
 
@@ -27,9 +28,11 @@ __global__ void __launch_bounds__(STEP_THREADS) k_run_frames(RunParams p) {
     __shared__ uint32_t s_line[FB_LINE_WORDS * STEP_THREADS];
     __shared__ uint32_t s_keys[10 * STEP_THREADS];
     const int tid = threadIdx.x;
-    const int tile = (blockIdx.x * STEP_THREADS + tid) >> 5, lane = tid & 31;
-    const int env = tile * GB_TILE + lane;
-    if (tile >= p.d.n_tiles || env >= p.d.n_envs) return;
+    const int warp = (blockIdx.x * STEP_THREADS + tid) >> 5, wl = tid & 31;
+    if (wl >= p.lanes) return;  // partial-warp mode: only the first `lanes` threads of each warp carry an env
+    const int env = warp * p.lanes + wl;
+    if (env >= p.d.n_envs) return;
+    const int tile = env >> 5, lane = env & 31;
     uint32_t *line = s_line + tid, *keys = s_keys + tid;
     const uint32_t ls = STEP_THREADS;
 
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_run_frames(RunParams p) {
         while (!done) {
             bool event;
             do {
-                uint32_t cycles = cpu_tick(m);
+                uint32_t cycles = cpu_step(m);
                 if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
                     int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
                     int c = a < b ? a : b;

@@ -35,9 +35,14 @@ struct gbenv {
     // staging for the *_host entry points
     uint8_t *d_actions = nullptr, *d_obs = nullptr, *d_done = nullptr;
     double *d_reward = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // CUDA-event ring: slot k holds {start, after k_run_frames, after k_wrap_*} of step k (mod EV_RING)
+    static const int EV_RING = 64;
+    cudaEvent_t ev[EV_RING][3] = {};
+    unsigned long long ev_step = 0, ev_folded = 0;  // steps recorded / steps folded into the totals
+    double ms_total[2] = {0.0, 0.0};
     bool ev_valid = false;
     unsigned long long launches = 0;
+    int lanes = 32;  // envs per warp in k_run_frames
     std::string err;
 };
 
@@ -257,7 +262,9 @@ extern "C" int gbenv_destroy(gbenv *h) {
     cudaFree(h->w.state); cudaFree(h->w.visited); cudaFree(h->w.counts_map);
     cudaFree(h->d_counters); cudaFree(h->d_stage_image); cudaFree(h->d_stage_buf); cudaFree(h->d_info_rows);
     cudaFree(h->d_env_ids); cudaFree(h->d_mask); cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_reward);
-    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &slot : h->ev)
+        for (auto &e : slot)
+            if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return GBENV_OK;
@@ -293,7 +300,7 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     ALLOC(h->d.lp, T * LP_WORDS);
     ALLOC(h->d.regs, T * R_WORDS);
     uint8_t *d_rom = nullptr;
-    ALLOC(d_rom, rom_len);
+    ALLOC(d_rom, rom_len + 16);  // padded: the instruction fetch reads two aligned words
     h->d.rom = d_rom;
     h->d.rom_banks = (uint32_t)(rom_len / 0x4000);
     h->d.n_envs = n_envs;
@@ -309,6 +316,18 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
         if (v >= 1 && v <= WRAP_MAPS) slots = v;
     }
     h->w.slots = slots;
+    {   // envs per warp: the interpreter is latency-bound, so spread a small batch over many warps.
+        // Aim for >= 16 warps per SM; GBENV_LANES overrides.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id);
+        int lanes = 32;
+        while (lanes > 1 && (n_envs + lanes - 1) / lanes < sms * 16) lanes >>= 1;
+        if (const char *ev = getenv("GBENV_LANES")) {
+            int v = atoi(ev);
+            if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
+        }
+        h->lanes = lanes;
+    }
     ALLOC(h->w.state, sizeof(WrapState) * (size_t)n_envs);
     ALLOC(h->w.visited, (size_t)n_envs * slots * per_slot);
     bool want_counts = (size_t)n_envs * COUNTS_H * COUNTS_W * 4 <= ((size_t)4 << 30);
@@ -322,7 +341,8 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     ALLOC(h->d_mask, (size_t)n_envs);
 #undef ALLOC
     CK(cudaStreamCreate(&h->stream));
-    for (auto &e : h->ev) CK(cudaEventCreate(&e));
+    for (auto &slot : h->ev)
+        for (auto &e : slot) CK(cudaEventCreate(&e));
     CK(cudaMemcpy(d_rom, rom_host, rom_len, cudaMemcpyHostToDevice));
     k_wrap_init<<<(n_envs + 127) / 128, 128, 0, h->stream>>>(h->w, n_envs);
     CK(cudaGetLastError());
@@ -333,6 +353,13 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     if (rc) { g_err = h->err; gbenv_destroy(h); return rc; }
     CK(cudaStreamSynchronize(h->stream));
     *out = h;
+    return GBENV_OK;
+}
+
+extern "C" int gbenv_set_lanes_per_warp(gbenv *h, int lanes) {
+    if (!h || !(lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
+        return fail(h, GBENV_E_ARG, "gbenv_set_lanes_per_warp: lanes must be a power of two in 1..32");
+    h->lanes = lanes;
     return GBENV_OK;
 }
 
@@ -414,7 +441,9 @@ static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int re
     p.render_mode = render_mode;
     p.release_frame = 8;
     p.counters = h->d_counters;
-    int blocks = (h->n_tiles * GB_TILE + STEP_THREADS - 1) / STEP_THREADS;
+    p.lanes = h->lanes;
+    int warps = (h->n + h->lanes - 1) / h->lanes;
+    int blocks = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
     k_run_frames<<<blocks, STEP_THREADS, 0, st>>>(p);
     h->launches++;
     CK(cudaGetLastError());
@@ -514,22 +543,43 @@ extern "C" int gbenv_reset(gbenv *h, const uint8_t *mask_host, int max_episode_s
     return GBENV_OK;
 }
 
+// accumulate the device time of recorded steps [ev_folded, upto) into ms_total (blocks on their events)
+static int fold_events(gbenv *h, unsigned long long upto) {
+    while (h->ev_folded < upto && h->ev_folded < h->ev_step) {
+        cudaEvent_t *ev = h->ev[h->ev_folded % gbenv::EV_RING];
+        CK(cudaEventSynchronize(ev[2]));
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+        h->ms_total[0] += a;
+        h->ms_total[1] += b;
+        h->ev_folded++;
+    }
+    return GBENV_OK;
+}
+
 extern "C" int gbenv_step(gbenv *h, const uint8_t *actions_dev, uint8_t *obs_dev, size_t obs_stride, double *reward_dev, uint8_t *done_dev,
                           void *stream) {
     if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev || obs_stride < GBENV_OBS_BYTES || (obs_stride & 3))
         return fail(h, GBENV_E_ARG, "gbenv_step: bad argument");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = pick(h, stream);
-    CK(cudaEventRecord(h->ev[0], st));
+    if (h->ev_step - h->ev_folded >= (unsigned long long)gbenv::EV_RING) {  // slot about to be reused: fold it first
+        int rcf = fold_events(h, h->ev_folded + 1);
+        if (rcf) return rcf;
+    }
+    cudaEvent_t *ev = h->ev[h->ev_step % gbenv::EV_RING];
+    CK(cudaEventRecord(ev[0], st));
     int rc = launch_run(h, actions_dev, GBENV_ACT_FREQ, 2, st);
     if (rc) return rc;
-    CK(cudaEventRecord(h->ev[1], st));
+    CK(cudaEventRecord(ev[1], st));
     int blocks = (h->n_tiles * GB_TILE + 127) / 128;
     k_wrap_step<<<blocks, 128, 0, st>>>(h->d, h->w, reward_dev, done_dev, h->d_info_rows);
     k_wrap_obs<<<h->n_tiles, 256, 0, st>>>(h->d, h->w, nullptr, obs_dev, obs_stride);
     h->launches += 2;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev[2], st));
+    CK(cudaEventRecord(ev[2], st));
+    h->ev_step++;
     h->ev_valid = true;
     return GBENV_OK;
 }
@@ -625,10 +675,21 @@ extern "C" int gbenv_get_counters(gbenv *h, gbenv_counters_t *out) {
 
 extern "C" int gbenv_last_kernel_ms(gbenv *h, int which, float *ms) {
     if (!h || !ms || which < 0 || which > 1) return fail(h, GBENV_E_ARG, "gbenv_last_kernel_ms: bad argument");
-    if (!h->ev_valid) return fail(h, GBENV_E_ARG, "gbenv_last_kernel_ms: no step recorded yet");
+    if (!h->ev_valid || h->ev_step == 0) return fail(h, GBENV_E_ARG, "gbenv_last_kernel_ms: no step recorded yet");
     CK(cudaSetDevice(h->device));
-    CK(cudaEventSynchronize(h->ev[2]));
-    CK(cudaEventElapsedTime(ms, h->ev[which], h->ev[which + 1]));
+    cudaEvent_t *ev = h->ev[(h->ev_step - 1) % gbenv::EV_RING];
+    CK(cudaEventSynchronize(ev[2]));
+    CK(cudaEventElapsedTime(ms, ev[which], ev[which + 1]));
+    return GBENV_OK;
+}
+
+extern "C" int gbenv_kernel_time_total(gbenv *h, int which, double *ms_total, uint64_t *steps) {
+    if (!h || which < 0 || which > 1 || !ms_total || !steps) return fail(h, GBENV_E_ARG, "gbenv_kernel_time_total: bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = fold_events(h, h->ev_step);
+    if (rc) return rc;
+    *ms_total = h->ms_total[which];
+    *steps = h->ev_folded;
     return GBENV_OK;
 }
 
