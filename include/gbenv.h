@@ -144,6 +144,10 @@ typedef struct gbenv_core_extra {
     int32_t reserved;
 } gbenv_core_extra_t;
 int gbenv_get_core_extra(gbenv_t *h, int env, gbenv_core_extra_t *out);
+/* Test hook for the PPU known-answer vectors: re-render all 144 lines of one env from its current VRAM /
+ * OAM / palettes using the stored per-scanline parameters (what PyBoy's renderer did for the frame a
+ * save-state embeds), into the env's framebuffer.  Synchronous.                                      */
+int gbenv_debug_render_frame(gbenv_t *h, int env);
 
 #ifdef __cplusplus
 }

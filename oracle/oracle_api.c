@@ -357,7 +357,7 @@ int oracle_wrapper_digest(oracle *h, int env, double *out, int n) {
 }
 
 /* Render one scanline of a freshly loaded state (PPU known-answer tests) */
-int oracle_render_frame_from_state(oracle *h, int env) {
+int oracle_debug_render_frame(oracle *h, int env) {
     if (!h || env < 0 || env >= h->n) return GBENV_E_ARG;
     GbCore *g = &h->envs[env].core;
     uint8_t scx = g->SCX, scy = g->SCY, wx = g->WX, wy = g->WY, lcdc = g->LCDC;

@@ -84,6 +84,7 @@ _SIGS = {
     "last_kernel_ms": ([C.c_void_p, C.c_int, C.POINTER(C.c_float)], C.c_int),
     "kernel_time_total": ([C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)], C.c_int),
     "get_core_extra": ([C.c_void_p, C.c_int, C.POINTER(CoreExtra)], C.c_int),
+    "debug_render_frame": ([C.c_void_p, C.c_int], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -243,6 +244,9 @@ class Handle:
         ms, steps = C.c_double(0), C.c_uint64(0)
         self._check(self.lib.kernel_time_total(self._h, int(which), C.byref(ms), C.byref(steps)), "kernel_time_total")
         return ms.value, steps.value
+
+    def debug_render_frame(self, env: int):
+        self._check(self.lib.debug_render_frame(self._h, int(env)), "debug_render_frame")
 
     def core_extra(self, env: int) -> CoreExtra:
         x = CoreExtra()

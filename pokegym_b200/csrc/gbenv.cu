@@ -708,3 +708,13 @@ extern "C" int gbenv_get_core_extra(gbenv *h, int env, gbenv_core_extra_t *out) 
     out->reserved = 0;
     return GBENV_OK;
 }
+
+extern "C" int gbenv_debug_render_frame(gbenv *h, int env) {
+    if (!h || env < 0 || env >= h->n) return fail(h, GBENV_E_ARG, "gbenv_debug_render_frame: bad argument");
+    CK(cudaSetDevice(h->device));
+    k_debug_render_frame<<<1, 1, 0, h->stream>>>(h->d, env);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return GBENV_OK;
+}

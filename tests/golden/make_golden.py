@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ (run in the build container, needs /root/reference).
+
+1. ref_wrapper_*.npz -- the UNMODIFIED reference `pokegym.Environment` stepped on the PyBoy shim
+   (tests/ref_shim.py) over the oracle emulator core with the synthetic Pokemon-like ROM: per-step reward
+   (float64), done, CRC32 of the (72,80,4) observation, SHA-256 of the full emulator state, the wrapper's
+   RAM writes, and the start state.  GPU tests replay the same actions through the CUDA path.
+2. ppu_kat.npz -- for a spread of the reference's own PyBoy save-states: the renderer inputs (VRAM, OAM,
+   LCD registers, per-scanline parameters) and the framebuffer PyBoy itself rendered from them (2 bits per
+   pixel).  These pin the scanline renderer to real PyBoy output.
+"""
+import hashlib
+import sys
+import zlib
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import __graft_entry__ as g  # noqa: E402
+from pokegym_b200 import _capi  # noqa: E402
+from pokegym_b200.state_file import parse_state  # noqa: E402
+from pokegym_b200.tools import synth_rom  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+REF = Path("/root/reference/pokegym")
+SHADE_OF = {0xFFFFFF01: 0, 0x99999900: 1, 0x55555500: 2, 0x00000000: 3}
+
+
+def wrapper_golden(name, rom_name, start_blob, n_steps, seed, max_episode_steps, reset_at, oracle_lib):
+    import ref_shim
+
+    rom_fn, kw = synth_rom.rom_catalog()[rom_name]
+    rom = rom_fn(**kw)
+    rng = np.random.default_rng(seed)
+    actions = rng.integers(0, 8, n_steps).astype(np.uint8)
+    ref = ref_shim.run_reference_episode(rom, oracle_lib, start_blob, actions, max_episode_steps=max_episode_steps, reset_at=reset_at)
+    obs_crc = np.array([zlib.crc32(o.tobytes()) for o in ref["obs"]], dtype=np.uint32)
+    state_sha = np.array([np.frombuffer(hashlib.sha256(s).digest(), dtype=np.uint8) for s in ref["states"]])
+    writes = np.array([len(w) for w in ref["writes"]], dtype=np.int32)
+    np.savez_compressed(
+        OUT / f"ref_wrapper_{name}.npz", rom_name=rom_name, start_state=np.frombuffer(start_blob, dtype=np.uint8), actions=actions,
+        rewards=np.array(ref["rewards"], dtype=np.float64), dones=np.array(ref["dones"], dtype=np.uint8), obs_crc=obs_crc, state_sha=state_sha,
+        n_ram_writes=writes, max_episode_steps=max_episode_steps, reset_at=np.array(reset_at, dtype=np.int32),
+        reset_obs_crc=np.array([zlib.crc32(o.tobytes()) for o in ref["reset_obs"]], dtype=np.uint32), last_obs=ref["obs"][-1])
+    print(name, "steps", n_steps, "sum|reward|", float(np.abs(ref["rewards"]).sum()), "nonzero rewards", int(np.count_nonzero(ref["rewards"])))
+
+
+def ppu_golden(n_pick=16):
+    files = sorted(p for p in REF.rglob("*") if p.is_file() and p.stat().st_size == 142_610)
+    # spread over the fixture directories; prefer states with a visible window / many sprites
+    pick = [files[i] for i in np.linspace(0, len(files) - 1, n_pick).astype(int)]
+    recs = dict(vram=[], oam=[], lcd_regs=[], scanline_params=[], fb2=[], names=[])
+    for p in pick:
+        st = parse_state(p.read_bytes())
+        words = np.frombuffer(st.raw["screen"].tobytes(), dtype="<u4")
+        shades = np.vectorize(SHADE_OF.__getitem__, otypes=[np.uint8])(words)
+        recs["vram"].append(st.raw["vram"])
+        recs["oam"].append(st.raw["oam"])
+        recs["lcd_regs"].append(st.raw["lcd_regs"])
+        recs["scanline_params"].append(st.raw["scanline_params"])
+        recs["fb2"].append(np.packbits(np.unpackbits(shades[:, None], axis=1)[:, 6:].reshape(-1)))  # 2 bits per pixel
+        recs["names"].append(str(p.relative_to(REF)))
+    np.savez_compressed(OUT / "ppu_kat.npz", **{k: np.array(v) for k, v in recs.items()})
+    print("ppu_kat:", len(pick), "fixtures")
+
+
+def main():
+    lib = _capi.GbEnvLib(g.build_oracle(), "oracle_")
+    rom = synth_rom.build_pokelike_rom()
+    h = _capi.Handle(lib, 1, rom)
+    h.tick(60, True)
+    start = h.save_state(0)
+    wrapper_golden("pokelike_a", "pokelike", start, 400, 11, 150, (150, 300), lib)
+    wrapper_golden("pokelike_b", "pokelike", start, 250, 12, 20480, (), lib)
+    ppu_golden()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""Shared helpers for the parity tests."""
+import hashlib
+import zlib
+from pathlib import Path
+
+import numpy as np
+
+from pokegym_b200 import _capi
+from pokegym_b200.state_file import field_offsets, parse_state, serialize_state
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+SHADE_WORDS = np.array([0xFFFFFF01, 0x99999900, 0x55555500, 0x00000000], dtype="<u4")
+
+
+def replay_wrapper_golden(handle, gold, xp=None, to_dev=lambda a: a, to_host=lambda a: a):
+    """Replays a ref_wrapper_*.npz recording through `handle` (oracle or CUDA) and checks every step."""
+    n = 1
+    start = gold["start_state"].tobytes()
+    tid = handle.add_state_template(start)
+    handle.set_initial_template(tid)
+    obs = to_dev(np.zeros((n, _capi.OBS_BYTES), dtype=np.uint8))
+    rew = to_dev(np.zeros(n, dtype=np.float64))
+    done = to_dev(np.zeros(n, dtype=np.uint8))
+    mes = int(gold["max_episode_steps"])
+    reset_at = set(int(x) for x in gold["reset_at"])
+    handle.reset(obs, max_episode_steps=mes)
+    assert zlib.crc32(to_host(obs).tobytes()) == int(gold["reset_obs_crc"][0]), "reset observation differs from the reference"
+    k = 1
+    for i, a in enumerate(gold["actions"]):
+        if i in reset_at:
+            handle.reset(obs, max_episode_steps=mes)
+            assert zlib.crc32(to_host(obs).tobytes()) == int(gold["reset_obs_crc"][k]), f"observation of reset #{k + 1} differs"
+            k += 1
+        handle.step(to_dev(np.array([a], dtype=np.uint8)), obs, rew, done)
+        r, d, o = float(to_host(rew)[0]), int(to_host(done)[0]), to_host(obs)
+        assert r == float(gold["rewards"][i]), f"step {i}: reward {r!r} != reference {float(gold['rewards'][i])!r}"
+        assert d == int(gold["dones"][i]), f"step {i}: done differs"
+        assert zlib.crc32(o.tobytes()) == int(gold["obs_crc"][i]), f"step {i}: observation differs from the reference"
+        if i % 25 == 0 or i == len(gold["actions"]) - 1:
+            sha = np.frombuffer(hashlib.sha256(handle.save_state(0)).digest(), dtype=np.uint8)
+            assert np.array_equal(sha, gold["state_sha"][i]), f"step {i}: emulator state differs (RAM side effects / emulation)"
+    assert np.array_equal(to_host(obs).reshape(72, 80, 4), gold["last_obs"])
+
+
+def ppu_kat_blob(base_blob: bytes, kat, i: int) -> bytes:
+    st = parse_state(base_blob)
+    st.raw["vram"] = kat["vram"][i]
+    st.raw["oam"] = kat["oam"][i]
+    st.raw["lcd_regs"] = kat["lcd_regs"][i]
+    st.raw["scanline_params"] = kat["scanline_params"][i]
+    return serialize_state(st)
+
+
+def ppu_kat_expected_screen(kat, i: int) -> bytes:
+    bits = np.unpackbits(kat["fb2"][i]).reshape(-1, 2)
+    shades = bits[:, 0] * 2 + bits[:, 1]
+    return SHADE_WORDS[shades].tobytes()
+
+
+def check_ppu_kat(handle, kat):
+    base = handle.save_state(0)
+    off, ln = field_offsets(9)["screen"]
+    for i in range(len(kat["names"])):
+        tid = handle.add_state_template(ppu_kat_blob(base, kat, i))
+        handle.load_template(tid)
+        handle.debug_render_frame(0)
+        got = handle.save_state(0)[off : off + ln]
+        assert got == ppu_kat_expected_screen(kat, i), f"PPU KAT {kat['names'][i]}: framebuffer differs from PyBoy's"

@@ -1,0 +1,89 @@
+"""The Python drop-in boundary on the GPU: Environment (single env, NumPy out) and VecEnvironment."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_environment_facade_matches_pokegym_signatures(cuda_lib, oracle_lib, roms):
+    from pokegym_b200 import Environment, _capi
+
+    rom = roms("pokelike")
+    env = Environment(rom_path=rom)
+    assert env.observation_space.shape == (72, 80, 4) and env.observation_space.dtype == np.uint8 and env.action_space.n == 8
+    obs, info = env.reset(max_episode_steps=5)
+    assert obs.shape == (72, 80, 4) and obs.dtype == np.uint8 and info == {}
+    cpu = _capi.Handle(oracle_lib, 1, rom)
+    cpu.tick(60, True)
+    o = np.zeros((1, _capi.OBS_BYTES), np.uint8)
+    r = np.zeros(1)
+    d = np.zeros(1, np.uint8)
+    cpu.reset(o, max_episode_steps=5)
+    assert np.array_equal(obs, o.reshape(72, 80, 4))
+    for s, a in enumerate([4, 0, 3, 6, 1]):
+        obs, rew, term, trunc, info = env.step(a)
+        cpu.step(np.array([a], np.uint8), o, r, d)
+        assert isinstance(rew, float) and rew == r[0] and term == trunc == bool(d[0])
+        assert np.array_equal(obs, o.reshape(72, 80, 4)) and np.array_equal(env.render(), obs)
+        assert bool(info) == (s == 4)
+    assert info["stats"]["step"] == 5 and "pokemon_exploration_map" in info and info["pokemon_exploration_map"].shape == (444, 436)
+    env.close()
+
+
+def test_vec_environment_rollout_and_auto_reset(cuda_lib, roms):
+    import torch
+
+    from pokegym_b200 import VecEnvironment
+    from pokegym_b200.puffer import PufferVecAdaptor
+
+    n, T = 96, 4
+    rollout = torch.zeros((T, n, 72, 80, 4), dtype=torch.uint8, device="cuda")
+    vec = VecEnvironment(n, roms("pokelike"), rollout=rollout, max_episode_steps=6, auto_reset=True)
+    obs, _ = vec.reset()
+    assert obs.data_ptr() == rollout[0].data_ptr()  # observations land in the rollout tensor, no copy
+    g = torch.Generator(device="cuda").manual_seed(0)
+    seen_done = False
+    for t in range(1, 9):
+        a = torch.randint(0, 8, (n,), generator=g, device="cuda", dtype=torch.uint8)
+        obs, rew, done, trunc, _ = vec.step(a)
+        assert obs.data_ptr() == rollout[t % T].data_ptr() and rew.dtype == torch.float64 and done.dtype == torch.bool
+        seen_done |= bool(done.all())
+    assert seen_done
+    s = vec.info_sum().cpu().numpy()
+    assert s[0] == n
+    ad = PufferVecAdaptor(vec)
+    ad.async_reset()
+    ad.send(torch.zeros(n, dtype=torch.uint8, device="cuda"))
+    flat, rew, term, trunc, infos, ids, mask = ad.recv()
+    assert flat.shape == (n, 23040) and len(ids) == n and mask.all()
+    vec.close()
+
+
+def test_mixed_initial_states(cuda_lib, oracle_lib, roms):
+    """BASELINE.json config 5 shape: env i resets from state i mod K (here K synthetic states)."""
+    import torch
+
+    from pokegym_b200 import VecEnvironment, _capi
+
+    rom = roms("pokelike")
+    src = _capi.Handle(oracle_lib, 1, rom)
+    blobs = []
+    for k in range(3):
+        src.tick(25 + 7 * k, True)
+        src.run_action(np.array([k], np.uint8))
+        blobs.append(src.save_state(0))
+    vec = VecEnvironment(7, rom, state_paths=blobs)
+    vec.reset()
+    for e in range(7):
+        assert vec.save_state(e) == _loaded(oracle_lib, rom, blobs[e % 3]), e
+    vec.close()
+
+
+def _loaded(oracle_lib, rom, blob):
+    from pokegym_b200 import _capi
+
+    h = _capi.Handle(oracle_lib, 1, rom)
+    h.set_initial_template(h.add_state_template(blob))
+    o = np.zeros((1, _capi.OBS_BYTES), np.uint8)
+    h.reset(o)
+    return h.save_state(0)

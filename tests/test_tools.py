@@ -1,0 +1,78 @@
+"""Host-side tooling: SM83 assembler, synthetic ROM generator, state-file codec."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from pokegym_b200.state_file import V9_LEN, diff_states, field_offsets, parse_state, serialize_state
+from pokegym_b200.tools import sm83asm, synth_rom
+
+
+def test_opcode_table_is_complete_and_unique():
+    base = {v[0][0] for v in sm83asm.OPTABLE.values() if len(v[0]) == 1}
+    cb = {v[0][1] for v in sm83asm.OPTABLE.values() if len(v[0]) == 2}
+    assert len(cb) == 256
+    assert base == set(range(256)) - set(sm83asm.ILLEGAL_OPCODES) - {0xCB}
+    assert len(sm83asm.OPTABLE) == 245 - 1 + 256  # 244 base mnemonics (CB prefix excluded) + the CB page
+
+
+def test_assembler_labels_and_relative_jumps():
+    rom = bytearray(0x8000)
+    a = sm83asm.Asm(rom)
+    a.org(0x150)
+    a.label("top")
+    a.i("LD A,n", 0x12)
+    a.i("JR NZ,e", "top")
+    a.i("JP nn", "top")
+    a.link()
+    assert bytes(rom[0x150:0x157]) == bytes([0x3E, 0x12, 0x20, 0xFC, 0xC3, 0x50, 0x01])
+
+
+def test_roms_are_deterministic_and_cover_every_opcode():
+    r1, r2 = synth_rom.build_pokelike_rom(), synth_rom.build_pokelike_rom()
+    assert r1 == r2 and len(r1) == 1 << 20
+    assert r1[0x147] == 0x13 and r1[0x20B3] == 0x76  # MBC3+RAM+BATTERY; HALT where Pokemon Red's DelayFrame halts
+    c = synth_rom.build_conformance_rom()
+    assert synth_rom.build_conformance_rom.last_missing == []
+    assert hashlib.sha256(c).hexdigest() == hashlib.sha256(synth_rom.build_conformance_rom()).hexdigest()
+
+
+def test_state_codec_round_trip_on_a_generated_state(oracle_lib, roms):
+    from pokegym_b200 import _capi
+
+    h = _capi.Handle(oracle_lib, 1, roms("pokelike"))
+    h.tick(30, True)
+    blob = h.save_state(0)
+    assert len(blob) == V9_LEN
+    st = parse_state(blob)
+    assert serialize_state(st) == blob
+    assert st.cpu["PC"] == 0x20B3 and st.cpu["halted"] == 1 and st.lcd["LY"] == 144
+    st.raw["wram"][0x123] ^= 0xFF
+    d = diff_states(blob, serialize_state(st))
+    assert d and d[0].startswith("wram: 1 bytes differ")
+    assert field_offsets(9)["joypad"] == (142_608, 2)
+
+
+def test_unsupported_blobs_are_rejected(oracle_lib, roms):
+    from pokegym_b200 import _capi
+
+    h = _capi.Handle(oracle_lib, 1, roms("pokelike"))
+    with pytest.raises(_capi.GbEnvError):
+        h.add_state_template(b"\x09" + bytes(100))
+    with pytest.raises(ValueError):
+        parse_state(bytes(10))
+
+
+def test_oracle_emulator_is_deterministic_and_actions_matter(oracle_lib, roms):
+    from pokegym_b200 import _capi
+
+    outs = []
+    for seed in (0, 0, 1):
+        h = _capi.Handle(oracle_lib, 2, roms("pokelike"))
+        h.tick(20, True)
+        rng = np.random.default_rng(seed)
+        for _ in range(8):
+            h.run_action(rng.integers(0, 8, 2).astype(np.uint8))
+        outs.append(h.save_state(1))
+        assert h.counters().faults == 0
+    assert outs[0] == outs[1] and outs[0] != outs[2]
