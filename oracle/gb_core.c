@@ -13,8 +13,10 @@
  * Call sites in the reference that reach this code:
  *   /root/reference/pokegym/pyboy_binding.py:44-91 (PyBoy(), send_input, _rendering, tick,
  *   load_state, screen_ndarray) and every get/set_memory_value in ram_map.py / environment.py.
- * Written as a big per-opcode switch on purpose: the CUDA product decodes by bit-fields over a
- * packed register file, so the two implementations share no structure and cross-check each other.
+ * One env at a time, byte-per-field state, a read/execute function per instruction group called
+ * straight through `gb_read`/`gb_write`.  The CUDA product is organised differently on purpose (packed
+ * register words, interleaved HBM arrays, one read site / one write site per instruction, LCD-event
+ * main loop, tile-wise 2-bpp renderer), so the two implementations cross-check each other.
  */
 #include "gb_core.h"
 
