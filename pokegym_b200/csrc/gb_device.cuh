@@ -44,8 +44,8 @@ struct Machine {
     uint32_t joy_dir, joy_std, lp_dirty, blank_shade;
     int ly_window;
     uint32_t hdr;
-    // statistics
-    uint32_t n_instr, n_cycles;
+    // statistics (n_cycles = clock delta + cyc_adj, see machine_store)
+    uint32_t n_instr, n_cycles, cyc_adj, clock0;
     // memory (pointers already offset to this env's lane inside its tile)
     uint8_t *memb;   // plain RAM, byte i at memb[((i >> 2) << 7) | (i & 3)]
     uint8_t *cramb;  // cart RAM, same addressing
@@ -105,10 +105,15 @@ __device__ inline void machine_load(Machine &m, const DevArrays &d, int tile, in
     m.blank_shade = r[R_MISC * 32] & 0xFF;
     m.n_instr = 0;
     m.n_cycles = 0;
+    m.cyc_adj = 0;
+    m.clock0 = m.clock;
 }
 
-__device__ inline void machine_store(const Machine &m, const DevArrays &d, int tile, int lane) {
+__device__ inline void machine_store(Machine &m, const DevArrays &d, int tile, int lane) {
     uint32_t *r = d.regs + il_index(tile, R_WORDS, 0, lane);
+    m.div = (m.div + (m.divc >> 8)) & 0xFF;  // DIV is kept lazily: fold the accumulated cycles (Timer.tick is additive)
+    m.divc &= 0xFF;
+    m.n_cycles = m.clock - m.clock0 + m.cyc_adj;
     r[R_BCDE * 32] = m.bcde;
     r[R_HLAF * 32] = m.hlaf;
     r[R_SPPC * 32] = (m.sp & 0xFFFF) | (m.pc << 16);
@@ -175,6 +180,7 @@ __device__ __forceinline__ void lcd_set_lcdc(Machine &m, uint32_t v) {
     if ((v ^ m.lcdc) & 0x10) m.lp_dirty = 144;
     m.lcdc = v;
     if (!(v & 0x80)) {
+        m.cyc_adj += m.clock;
         m.clock = 0;
         m.target = FRAME_CYCLES;
         stat_set_mode(m, 0);
@@ -363,11 +369,28 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
     m.blank_shade = 0xFF;
 }
 
-__device__ inline void lcd_blank_screen(Machine &m) {
+// Out-of-line entry points of the renderer: inputs by value, so the caller's Machine stays in registers
+// and the (large) renderer body is kept out of the interpreter's hot loop.
+__device__ __noinline__ int render_line_out(uint8_t *memb, uint32_t *fb, uint32_t a /* lcdc | scy<<8 | scx<<16 | bgp<<24 */,
+                                            uint32_t b /* wy | wx<<8 | obp0<<16 | obp1<<24 */, int ly_window, uint32_t y, uint32_t *line,
+                                            uint32_t *keys, uint32_t ls) {
+    Machine r;
+    r.memb = memb; r.fb = fb;
+    r.lcdc = a & 0xFF; r.scy = (a >> 8) & 0xFF; r.scx = (a >> 16) & 0xFF; r.bgp = a >> 24;
+    r.wy = b & 0xFF; r.wx = (b >> 8) & 0xFF; r.obp0 = (b >> 16) & 0xFF; r.obp1 = b >> 24;
+    r.ly_window = ly_window;
+    render_line(r, y, line, keys, ls);
+    return r.ly_window;
+}
+
+__device__ __noinline__ void fill_framebuffer(uint32_t *fb, uint32_t fill) {
+    for (uint32_t k = 0; k < FB_WORDS; k++) fb[k << 5] = fill;
+}
+
+__device__ __forceinline__ void lcd_blank_screen(Machine &m) {
     uint32_t shade = pal_shade(m.bgp, 0);
     if (m.blank_shade == shade) return;  // already uniformly this shade: the refill would be a no-op
-    uint32_t fill = shade * 0x55555555u;
-    for (uint32_t k = 0; k < FB_WORDS; k++) m.fb[k << 5] = fill;
+    fill_framebuffer(m.fb, shade * 0x55555555u);
     m.blank_shade = shade;
 }
 
@@ -379,6 +402,7 @@ __device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uin
         case 2:
             if (m.ly == 153) {
                 m.ly = 0;
+                m.cyc_adj += m.clock - m.clock % FRAME_CYCLES;
                 m.clock %= FRAME_CYCLES;
                 m.target %= FRAME_CYCLES;
             } else {
@@ -400,7 +424,11 @@ __device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uin
                     m.lp[m.ly << 5] = v;
                     m.lp_dirty--;
                 }
-                if (!m.disable_renderer) render_line(m, m.ly, line, keys, ls);
+                if (!m.disable_renderer) {
+                    m.ly_window = render_line_out(m.memb, m.fb, m.lcdc | (m.scy << 8) | (m.scx << 16) | (m.bgp << 24),
+                                                  m.wy | (m.wx << 8) | (m.obp0 << 16) | (m.obp1 << 24), m.ly_window, m.ly, line, keys, ls);
+                    m.blank_shade = 0xFF;
+                }
             }
             m.next_mode = (m.ly < 143) ? 2 : 1;
             break;
@@ -419,6 +447,7 @@ __device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uin
         m.iflag |= irq;
     } else {
         m.frame_done = 1;
+        m.cyc_adj += m.clock - m.clock % FRAME_CYCLES;
         m.clock %= FRAME_CYCLES;
         lcd_blank_screen(m);
     }
@@ -431,9 +460,7 @@ __device__ __forceinline__ uint32_t timer_divider(uint32_t tac) {
 }
 
 __device__ __forceinline__ void timer_tick(Machine &m, uint32_t cycles) {
-    m.divc += cycles;
-    m.div = (m.div + (m.divc >> 8)) & 0xFF;
-    m.divc &= 0xFF;
+    m.divc += cycles;  // DIV = div + (divc >> 8), materialised on read / store
     if (m.tac & 4) {
         m.timac += cycles;
         uint32_t dv = timer_divider(m.tac);
@@ -455,129 +482,138 @@ __device__ __forceinline__ int timer_cycles_to_interrupt(const Machine &m) {
 }
 
 // --------------------------------------------------------------------------------------------- bus
-// Two flavours of every bus function:
-//   *_full  : everything inline.  Used by the interpreter, which funnels ALL of an instruction's data
-//             accesses through one read site and one write site (cpu_step), so the big IO switch is
-//             instantiated once and `Machine` never has its address taken (it stays in registers).
-//   bus_read / bus_write : small inline fast path + out-of-line slow path, for the wrapper kernels and
-//             the debug bus access, where call-site count matters more than register residency.
+// The interpreter (gb_cpu.cuh) defers all stores of an instruction to one write site; its read and write
+// sites inline only the hot regions (WRAM, ROM, HRAM, VRAM, OAM); IO registers, MBC
+// registers, cart RAM and OAM DMA live in out-of-line functions that take their inputs BY VALUE (reads) or
+// work on a scratch copy of the machine (writes), so `Machine` itself never has its address taken and
+// stays in registers, and the hot loop stays small (the kernel is instruction-cache sensitive).
 
-#define BUS_READ_BODY                                                                        \
-    if (a < 0xFF00) {                                                                        \
-        if (a >= 0xFE00) return mem_rd(m, MEM_HI + (a - 0xFE00));                            \
-        if (a >= 0xC000) return mem_rd(m, MEM_WRAM + (a & 0x1FFF)); /* WRAM + echo */       \
-        if (a >= 0xA000) {                                                                   \
-            if (!m.ram_en) return 0xFF;                                                      \
-            uint32_t i = (m.rambank & 3) * 0x2000u + (a - 0xA000);                           \
-            return m.cramb[((i >> 2) << 7) | (i & 3)];                                       \
-        }                                                                                    \
-        return mem_rd(m, MEM_VRAM + (a - 0x8000));                                           \
-    }                                                                                        \
-    if (a >= 0xFF80 && a < 0xFFFF) return mem_rd(m, MEM_HI + (a - 0xFE00)); /* HRAM */       \
-    switch (a) {                                                                             \
-    case 0xFF04: return m.div;                                                               \
-    case 0xFF05: return m.tima;                                                              \
-    case 0xFF06: return m.tma;                                                               \
-    case 0xFF07: return m.tac;                                                               \
-    case 0xFF0F: return m.iflag;                                                             \
-    case 0xFF40: return m.lcdc;                                                              \
-    case 0xFF41: return m.stat;                                                              \
-    case 0xFF42: return m.scy;                                                               \
-    case 0xFF43: return m.scx;                                                               \
-    case 0xFF44: return m.ly;                                                                \
-    case 0xFF45: return m.lyc;                                                               \
-    case 0xFF46: return 0;                                                                   \
-    case 0xFF47: return m.bgp;                                                               \
-    case 0xFF48: return m.obp0;                                                              \
-    case 0xFF49: return m.obp1;                                                              \
-    case 0xFF4A: return m.wy;                                                                \
-    case 0xFF4B: return m.wx;                                                                \
-    case 0xFFFF: return m.ie;                                                                \
-    default:                                                                                 \
-        if (a >= 0xFF10 && a < 0xFF40) return 0; /* sound disabled (pokegym default) */      \
-        return mem_rd(m, MEM_HI + (a - 0xFE00));                                             \
+#define IO_NOT_A_REGISTER 0x100u
+// value of an IO register modelled outside the IO array, or IO_NOT_A_REGISTER
+__device__ __noinline__ uint32_t io_reg_read(uint32_t a, uint32_t lcd0, uint32_t lcd1, uint32_t pal_ie, uint32_t tim, uint32_t iflag) {
+    switch (a) {
+    case 0xFF04: return tim & 0xFF;
+    case 0xFF05: return (tim >> 8) & 0xFF;
+    case 0xFF06: return (tim >> 16) & 0xFF;
+    case 0xFF07: return tim >> 24;
+    case 0xFF0F: return iflag;
+    case 0xFF40: return lcd0 & 0xFF;
+    case 0xFF41: return (lcd0 >> 8) & 0xFF;
+    case 0xFF42: return lcd1 & 0xFF;
+    case 0xFF43: return (lcd1 >> 8) & 0xFF;
+    case 0xFF44: return (lcd0 >> 16) & 0xFF;
+    case 0xFF45: return lcd0 >> 24;
+    case 0xFF46: return 0;
+    case 0xFF47: return pal_ie & 0xFF;
+    case 0xFF48: return (pal_ie >> 8) & 0xFF;
+    case 0xFF49: return (pal_ie >> 16) & 0xFF;
+    case 0xFF4A: return (lcd1 >> 16) & 0xFF;
+    case 0xFF4B: return lcd1 >> 24;
+    case 0xFFFF: return pal_ie >> 24;
+    default: return (a >= 0xFF10 && a < 0xFF40) ? 0u : IO_NOT_A_REGISTER;  // sound disabled (pokegym default): reads 0
     }
+}
 
 __device__ __forceinline__ uint32_t bus_read_full(Machine &m, uint32_t a) {  // Motherboard.getitem
+    if (a - 0xC000u < 0x3E00u) return mem_rd(m, MEM_WRAM + (a & 0x1FFF));  // WRAM and its echo
     if (a < 0x8000) return __ldg(m.rom + (a < 0x4000 ? a : a + m.rom_off));
-    BUS_READ_BODY
+    if (a >= 0xFF80 && a != 0xFFFF) return mem_rd(m, MEM_HI + (a - 0xFE00));  // HRAM
+    if (a < 0xA000) return mem_rd(m, MEM_VRAM + (a - 0x8000));
+    if (a < 0xC000) {
+        if (!m.ram_en) return 0xFF;
+        uint32_t i = (m.rambank & 3) * 0x2000u + (a - 0xA000);
+        return m.cramb[((i >> 2) << 7) | (i & 3)];
+    }
+    if (a >= 0xFF00) {
+        uint32_t r = io_reg_read(a, m.lcdc | (m.stat << 8) | (m.ly << 16) | (m.lyc << 24), m.scy | (m.scx << 8) | (m.wy << 16) | (m.wx << 24),
+                                 m.bgp | (m.obp0 << 8) | (m.obp1 << 16) | (m.ie << 24),
+                                 ((m.div + (m.divc >> 8)) & 0xFF) | (m.tima << 8) | (m.tma << 16) | (m.tac << 24), m.iflag);
+        if (r != IO_NOT_A_REGISTER) return r;
+    }
+    return mem_rd(m, MEM_HI + (a - 0xFE00));  // OAM, 0xFEA0-0xFEFF, plain IO array bytes
 }
-__device__ __noinline__ uint32_t bus_read_slow(Machine &m, uint32_t a) { BUS_READ_BODY }
-__device__ __forceinline__ uint32_t bus_read(Machine &m, uint32_t a) {
+__device__ __noinline__ uint32_t bus_read_slow(Machine &m, uint32_t a) { return bus_read_full(m, a); }
+__device__ __forceinline__ uint32_t bus_read(Machine &m, uint32_t a) {  // wrapper kernels / debug access
     if (a < 0x8000) return __ldg(m.rom + (a < 0x4000 ? a : a + m.rom_off));
     if (a >= 0xC000 && a < 0xE000) return mem_rd(m, MEM_WRAM + (a - 0xC000));
     return bus_read_slow(m, a);
 }
 
-// Motherboard.transfer_DMA: instantaneous copy of 0xA0 bytes to OAM
-__device__ __forceinline__ void oam_dma(Machine &m, uint32_t page);
-__device__ __forceinline__ uint32_t bus_read_full(Machine &m, uint32_t a);
-__device__ __forceinline__ void oam_dma(Machine &m, uint32_t page) {
-    uint32_t src = page << 8;
-    bool plain = (page >= 0x80 && page < 0xA0) || (page >= 0xC0 && page < 0xFE);
-    if (plain) {  // word copy inside the plain-RAM array (src is 256-byte aligned)
-        uint32_t base = page < 0xA0 ? (MEM_VRAM + (src - 0x8000)) : (MEM_WRAM + (src & 0x1FFF));
-        for (uint32_t k = 0; k < 40; k++) mem_wr_word(m, (MEM_HI >> 2) + k, mem_rd_word(m, (base >> 2) + k));
-    } else {
-        for (uint32_t k = 0; k < 160; k++) mem_wr(m, MEM_HI + k, bus_read_full(m, (src + k) & 0xFFFF));
+// Everything a store can do besides hitting plain RAM: MBC3 registers, cart RAM, IO registers, OAM DMA.
+__device__ __noinline__ void bus_write_rare(Machine *mp, uint32_t a, uint32_t v) {
+    Machine &m = *mp;
+    if (a < 0x8000) {  // MBC3 registers
+        if (a < 0x2000) {
+            if ((v & 0x0F) == 0x0A) m.ram_en = 1;
+            else if (v == 0) m.ram_en = 0;  // PyBoy: any other value leaves the latch untouched
+        } else if (a < 0x4000) {
+            v &= 0x7F;
+            machine_set_rombank(m, v ? v : 1);
+        } else if (a < 0x6000) {
+            m.rambank = v;
+        }
+        return;
+    }
+    if (a < 0xA000) { mem_wr(m, MEM_VRAM + (a - 0x8000), v); return; }
+    if (a < 0xC000) {  // 0xA000-0xBFFF cart RAM
+        if (m.ram_en && m.rambank <= 3) {
+            uint32_t i = m.rambank * 0x2000u + (a - 0xA000);
+            m.cramb[((i >> 2) << 7) | (i & 3)] = (uint8_t)v;
+        }
+        return;
+    }
+    if (a < 0xFE00) { mem_wr(m, MEM_WRAM + (a & 0x1FFF), v); return; }  // WRAM / echo (only reached through bus_write)
+    if (a < 0xFF00 || (a >= 0xFF80 && a != 0xFFFF)) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }
+    switch (a) {
+    case 0xFF00: mem_wr(m, MEM_HI + 0x100, joypad_pull(m, v)); break;
+    case 0xFF04: m.div = 0; m.divc = 0; m.timac = 0; break;
+    case 0xFF05: m.tima = v; break;
+    case 0xFF06: m.tma = v; break;
+    case 0xFF07: m.tac = v & 7; break;
+    case 0xFF0F: m.iflag = v; break;
+    case 0xFF40: lcd_set_lcdc(m, v); break;
+    case 0xFF41: m.stat = (m.stat & 0x87) | (v & 0x78); break;
+    case 0xFF42: if (v != m.scy) m.lp_dirty = 144; m.scy = v; break;
+    case 0xFF43: if (v != m.scx) m.lp_dirty = 144; m.scx = v; break;
+    case 0xFF44: m.ly = v; m.lp_dirty = 144; break;  // PyBoy lets LY be written
+    case 0xFF45: m.lyc = v; break;
+    case 0xFF46: {  // Motherboard.transfer_DMA: instantaneous copy of 0xA0 bytes to OAM
+        uint32_t src = v << 8;
+        bool plain = (v >= 0x80 && v < 0xA0) || (v >= 0xC0 && v < 0xFE);
+        if (plain) {  // word copy inside the plain-RAM array (src is 256-byte aligned)
+            uint32_t base = v < 0xA0 ? (MEM_VRAM + (src - 0x8000)) : (MEM_WRAM + (src & 0x1FFF));
+            for (uint32_t k = 0; k < 40; k++) mem_wr_word(m, (MEM_HI >> 2) + k, mem_rd_word(m, (base >> 2) + k));
+        } else {
+            for (uint32_t k = 0; k < 160; k++) mem_wr(m, MEM_HI + k, bus_read_full(m, (src + k) & 0xFFFF));
+        }
+        break;
+    }
+    case 0xFF47: m.bgp = v; break;
+    case 0xFF48: m.obp0 = v; break;
+    case 0xFF49: m.obp1 = v; break;
+    case 0xFF4A: if (v != m.wy) m.lp_dirty = 144; m.wy = v; break;
+    case 0xFF4B: if (v != m.wx) m.lp_dirty = 144; m.wx = v; break;
+    case 0xFFFF: m.ie = v; break;
+    default:
+        if (a >= 0xFF10 && a < 0xFF40) break;  // sound disabled: writes dropped
+        mem_wr(m, MEM_HI + (a - 0xFE00), v);
+        break;
     }
 }
 
-#define BUS_WRITE_BODY                                                                                    \
-    v &= 0xFF;                                                                                            \
-    if (a >= 0xC000 && a < 0xFE00) { mem_wr(m, MEM_WRAM + (a & 0x1FFF), v); return; }                     \
-    if (a < 0x8000) { /* MBC3 registers */                                                                \
-        if (a < 0x2000) {                                                                                 \
-            if ((v & 0x0F) == 0x0A) m.ram_en = 1;                                                         \
-            else if (v == 0) m.ram_en = 0; /* PyBoy: any other value leaves the latch untouched */        \
-        } else if (a < 0x4000) {                                                                          \
-            v &= 0x7F;                                                                                    \
-            machine_set_rombank(m, v ? v : 1);                                                            \
-        } else if (a < 0x6000) {                                                                          \
-            m.rambank = v;                                                                                \
-        }                                                                                                 \
-        return;                                                                                           \
-    }                                                                                                     \
-    if (a < 0xA000) { mem_wr(m, MEM_VRAM + (a - 0x8000), v); return; }                                    \
-    if (a < 0xC000) {                                                                                     \
-        if (m.ram_en && m.rambank <= 3) {                                                                 \
-            uint32_t i = m.rambank * 0x2000u + (a - 0xA000);                                              \
-            m.cramb[((i >> 2) << 7) | (i & 3)] = (uint8_t)v;                                              \
-        }                                                                                                 \
-        return;                                                                                           \
-    }                                                                                                     \
-    if (a < 0xFF00 || (a >= 0xFF80 && a < 0xFFFF)) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }       \
-    switch (a) {                                                                                          \
-    case 0xFF00: mem_wr(m, MEM_HI + 0x100, joypad_pull(m, v)); break;                                     \
-    case 0xFF04: m.div = 0; m.divc = 0; m.timac = 0; break;                                               \
-    case 0xFF05: m.tima = v; break;                                                                       \
-    case 0xFF06: m.tma = v; break;                                                                        \
-    case 0xFF07: m.tac = v & 7; break;                                                                    \
-    case 0xFF0F: m.iflag = v; break;                                                                      \
-    case 0xFF40: lcd_set_lcdc(m, v); break;                                                               \
-    case 0xFF41: m.stat = (m.stat & 0x87) | (v & 0x78); break;                                            \
-    case 0xFF42: if (v != m.scy) m.lp_dirty = 144; m.scy = v; break;                                      \
-    case 0xFF43: if (v != m.scx) m.lp_dirty = 144; m.scx = v; break;                                      \
-    case 0xFF44: m.ly = v; m.lp_dirty = 144; break; /* PyBoy lets LY be written */                        \
-    case 0xFF45: m.lyc = v; break;                                                                        \
-    case 0xFF46: oam_dma(m, v); break;                                                                    \
-    case 0xFF47: m.bgp = v; break;                                                                        \
-    case 0xFF48: m.obp0 = v; break;                                                                       \
-    case 0xFF49: m.obp1 = v; break;                                                                       \
-    case 0xFF4A: if (v != m.wy) m.lp_dirty = 144; m.wy = v; break;                                        \
-    case 0xFF4B: if (v != m.wx) m.lp_dirty = 144; m.wx = v; break;                                        \
-    case 0xFFFF: m.ie = v; break;                                                                         \
-    default:                                                                                              \
-        if (a >= 0xFF10 && a < 0xFF40) break; /* sound disabled: writes dropped */                        \
-        mem_wr(m, MEM_HI + (a - 0xFE00), v);                                                              \
-        break;                                                                                            \
-    }
-
-__device__ __forceinline__ void bus_write_full(Machine &m, uint32_t a, uint32_t v) { BUS_WRITE_BODY }  // Motherboard.setitem
-__device__ __noinline__ void bus_write_slow(Machine &m, uint32_t a, uint32_t v) { BUS_WRITE_BODY }
-__device__ __forceinline__ void bus_write(Machine &m, uint32_t a, uint32_t v) {
+__device__ __forceinline__ void bus_write_full(Machine &m, uint32_t a, uint32_t v) {  // Motherboard.setitem
+    v &= 0xFF;
+    if (a - 0xC000u < 0x3E00u) { mem_wr(m, MEM_WRAM + (a & 0x1FFF), v); return; }
+    if ((a >= 0xFF80 && a != 0xFFFF) || (a >= 0xFE00 && a < 0xFF00)) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }
+    if (a - 0x8000u < 0x2000u) { mem_wr(m, MEM_VRAM + (a - 0x8000), v); return; }
+    Machine t = m;  // rare: work on a scratch copy so that `m` keeps living in registers
+    bus_write_rare(&t, a, v);
+    m = t;
+}
+__device__ __forceinline__ void bus_write(Machine &m, uint32_t a, uint32_t v) {  // wrapper kernels / debug access
+    v &= 0xFF;
     if (a >= 0xC000 && a < 0xE000) mem_wr(m, MEM_WRAM + (a - 0xC000), v);
-    else bus_write_slow(m, a, v);
+    else bus_write_rare(&m, a, v);
 }
 
 // ------------------------------------------------------------------------------------------- SM83
@@ -635,322 +671,4 @@ __device__ __forceinline__ void alu8(Machine &m, uint32_t op, uint32_t v) {
         nf = (op == 4 ? FLAG_H : 0) | (res == 0 ? FLAG_Z : 0);
     }
     set_af(m, res, nf);
-}
-
-// Instruction fetch: opcode plus its two possible operand bytes as one little-endian word.  Code almost
-// always runs from cartridge ROM, where the three bytes come from two aligned 32-bit read-only loads
-// (the ROM image is padded, so the second load is always in bounds); RAM code takes the byte path.
-__device__ __forceinline__ uint32_t fetch3(Machine &m, uint32_t pc) {
-    if (pc < 0x7FFD && (pc & 0x3FFF) < 0x3FFD) {  // the whole instruction lies inside one ROM bank window
-        uint32_t addr = pc < 0x4000 ? pc : pc + m.rom_off;
-        const uint32_t *w = (const uint32_t *)(m.rom + (addr & ~3u));
-        return __funnelshift_r(__ldg(w), __ldg(w + 1), (addr & 3) * 8);
-    }
-    uint32_t ins = 0;
-    for (uint32_t i = 0; i < 3; i++) ins |= bus_read_full(m, (pc + i) & 0xFFFF) << (8 * i);
-    return ins;
-}
-
-// CPU.tick: interrupt check, HALT handling, one instruction.  Returns T-cycles (pastraiser table as used
-// by PyBoy; interrupt dispatch costs 0).  Every data access of the instruction goes through ONE read
-// site (up to two consecutive bytes: operand or 16-bit pop) and ONE write site (up to two bytes: operand,
-// 16-bit push or LD (nn),SP), so threads executing different opcodes still share the memory code.
-__device__ __forceinline__ uint32_t cpu_step(Machine &m) {
-    uint32_t wn = 0, w0a = 0, w0v = 0, w1a = 0, w1v = 0;  // deferred bus writes, issued in order w0, w1
-    uint32_t cycles = 0;
-#define PUSH16(val)                                  \
-    do {                                             \
-        uint32_t _v = (val);                         \
-        w0a = (m.sp - 1) & 0xFFFF; w0v = _v >> 8;    \
-        w1a = (m.sp - 2) & 0xFFFF; w1v = _v & 0xFF;  \
-        wn = 2;                                      \
-        m.sp = (m.sp - 2) & 0xFFFF;                  \
-    } while (0)
-#define WRITE8(addr, val) do { w0a = (addr) & 0xFFFF; w0v = (val); wn = 1; } while (0)
-
-    bool execute = true;
-    if (!m.iq) {
-        uint32_t pending = m.iflag & m.ie & 0x1F;
-        if (pending) {  // CPU.handle_interrupt for the highest-priority pending source
-            uint32_t bit = pending & (0u - pending);
-            if (m.halted) m.pc = (m.pc + 1) & 0xFFFF;
-            if (m.ime) {
-                m.iflag ^= bit;
-                PUSH16(m.pc);
-                m.pc = 0x40 + 8 * (31 - __clz(bit));
-                m.ime = 0;
-            }
-            m.iq = 1;
-            m.halted = 0;
-            execute = false;  // PyBoy charges no cycles for the dispatch
-        }
-    } else if (m.halted) {  // debugger-only path in PyBoy: halted with a queued interrupt
-        m.halted = 0;
-        m.pc = (m.pc + 1) & 0xFFFF;
-    }
-    if (execute && m.halted) return 4;
-    if (execute) {
-        const uint32_t pc = m.pc;
-        const uint32_t ins = fetch3(m, pc);
-        const uint32_t op = ins & 0xFF, imm8 = (ins >> 8) & 0xFF, imm16 = (ins >> 8) & 0xFFFF;
-        const bool cb = op == 0xCB;
-        const uint32_t dop = cb ? imm8 : op;  // the byte whose x/y/z fields select the operation
-        const uint32_t x = dop >> 6, y = (dop >> 3) & 7, z = dop & 7, p = y >> 1, q = y & 1;
-        const uint32_t hl = reg_hl(m);
-        // ---- read phase: which bytes does this instruction load?
-        uint32_t rn = 0, ra = hl;
-        if (cb) {
-            rn = z == 6;
-        } else if (x == 0) {
-            if ((z == 4 || z == 5) && y == 6) rn = 1;
-            else if (z == 2 && q == 1) { rn = 1; ra = p == 0 ? (m.bcde & 0xFFFF) : p == 1 ? (m.bcde >> 16) : hl; }
-        } else if (x == 1 || x == 2) {
-            rn = (z == 6 && op != 0x76);
-        } else {
-            if (z == 0) {
-                if (y < 4) { if (condition(m, y)) { rn = 2; ra = m.sp; } }
-                else if (y == 6) { rn = 1; ra = 0xFF00 + imm8; }
-            } else if (z == 1) {
-                if (q == 0 || p < 2) { rn = 2; ra = m.sp; }
-            } else if (z == 2) {
-                if (y == 6) { rn = 1; ra = 0xFF00 + (m.bcde & 0xFF); }
-                else if (y == 7) { rn = 1; ra = imm16; }
-            }
-        }
-        uint32_t rv = 0;
-        for (uint32_t i = 0; i < rn; i++) rv |= bus_read_full(m, (ra + i) & 0xFFFF) << (8 * i);
-        // ---- execute phase (registers only)
-#define NEXT(n) m.pc = (pc + (n)) & 0xFFFF
-        if (cb) {
-            NEXT(2);
-            uint32_t v = (z == 6) ? rv : reg8(m, z), f = reg_f(m), res;
-            cycles = z == 6 ? 16 : 8;  // PyBoy's table charges 16 for BIT b,(HL) as well
-            if (x == 1) {  // BIT: Z from the tested bit, H set, C kept
-                set_f(m, (f & FLAG_C) | FLAG_H | (((v >> y) & 1) ? 0 : FLAG_Z));
-            } else {
-                if (x == 0) {
-                    uint32_t c = (f >> 4) & 1, cout;
-                    switch (y) {
-                    case 0: cout = v >> 7; res = (v << 1) | cout; break;        // RLC
-                    case 1: cout = v & 1; res = (v >> 1) | (cout << 7); break;  // RRC
-                    case 2: cout = v >> 7; res = (v << 1) | c; break;           // RL
-                    case 3: cout = v & 1; res = (v >> 1) | (c << 7); break;     // RR
-                    case 4: cout = v >> 7; res = v << 1; break;                 // SLA
-                    case 5: cout = v & 1; res = (v >> 1) | (v & 0x80); break;   // SRA
-                    case 6: cout = 0; res = (v >> 4) | (v << 4); break;         // SWAP
-                    default: cout = v & 1; res = v >> 1; break;                 // SRL
-                    }
-                    res &= 0xFF;
-                    set_f(m, (res == 0 ? FLAG_Z : 0) | (cout ? FLAG_C : 0));
-                } else {
-                    res = (x == 2) ? (v & ~(1u << y)) : (v | (1u << y));  // RES / SET
-                }
-                if (z == 6) WRITE8(hl, res);
-                else set_reg8(m, z, res);
-            }
-        } else if (x == 1) {
-            if (op == 0x76) {  // HALT: PC stays on the HALT byte, wake-up adds 1
-                m.halted = 1;
-                cycles = 4;
-            } else {
-                uint32_t v = (z == 6) ? rv : reg8(m, z);
-                if (y == 6) WRITE8(hl, v);
-                else set_reg8(m, y, v);
-                NEXT(1);
-                cycles = (y == 6 || z == 6) ? 8 : 4;
-            }
-        } else if (x == 2) {
-            alu8(m, y, (z == 6) ? rv : reg8(m, z));
-            NEXT(1);
-            cycles = z == 6 ? 8 : 4;
-        } else if (x == 0) {
-            switch (z) {
-            case 0:
-                if (y == 0) { NEXT(1); cycles = 4; }
-                else if (y == 1) {  // LD (nn),SP: low byte first
-                    w0a = imm16; w0v = m.sp & 0xFF; w1a = (imm16 + 1) & 0xFFFF; w1v = m.sp >> 8; wn = 2;
-                    NEXT(3);
-                    cycles = 20;
-                } else if (y == 2) { NEXT(2); cycles = 4; }  // STOP
-                else if (y == 3 || condition(m, y - 4)) {  // JR
-                    m.pc = (pc + 2 + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;
-                    cycles = 12;
-                } else { NEXT(2); cycles = 8; }
-                break;
-            case 1:
-                if (q == 0) {
-                    set_reg_pair(m, p, imm16);
-                    NEXT(3);
-                    cycles = 12;
-                } else {  // ADD HL,rp
-                    uint32_t v = reg_pair(m, p), t = hl + v;
-                    set_f(m, (reg_f(m) & FLAG_Z) | (((hl & 0xFFF) + (v & 0xFFF)) > 0xFFF ? FLAG_H : 0) | (t > 0xFFFF ? FLAG_C : 0));
-                    set_hl(m, t);
-                    NEXT(1);
-                    cycles = 8;
-                }
-                break;
-            case 2: {
-                uint32_t a = (p == 0) ? (m.bcde & 0xFFFF) : (p == 1) ? (m.bcde >> 16) : hl;
-                if (q == 0) WRITE8(a, reg_a(m));
-                else set_a(m, rv);
-                if (p == 2) set_hl(m, a + 1);
-                else if (p == 3) set_hl(m, a - 1);
-                NEXT(1);
-                cycles = 8;
-                break;
-            }
-            case 3:
-                set_reg_pair(m, p, reg_pair(m, p) + (q ? 0xFFFFu : 1u));
-                NEXT(1);
-                cycles = 8;
-                break;
-            case 4:
-            case 5: {  // INC r / DEC r
-                uint32_t v = (y == 6) ? rv : reg8(m, y), res, nf = reg_f(m) & FLAG_C;
-                if (z == 4) {
-                    res = (v + 1) & 0xFF;
-                    nf |= ((v & 0xF) == 0xF ? FLAG_H : 0);
-                } else {
-                    res = (v - 1) & 0xFF;
-                    nf |= FLAG_N | ((v & 0xF) == 0 ? FLAG_H : 0);
-                }
-                if (res == 0) nf |= FLAG_Z;
-                set_f(m, nf);
-                if (y == 6) WRITE8(hl, res);
-                else set_reg8(m, y, res);
-                NEXT(1);
-                cycles = y == 6 ? 12 : 4;
-                break;
-            }
-            case 6:
-                if (y == 6) WRITE8(hl, imm8);
-                else set_reg8(m, y, imm8);
-                NEXT(2);
-                cycles = y == 6 ? 12 : 8;
-                break;
-            default: {
-                uint32_t a = reg_a(m), f = reg_f(m), c = (f >> 4) & 1;
-                switch (y) {
-                case 0: set_af(m, (a << 1) | (a >> 7), (a >> 7) ? FLAG_C : 0); break;  // RLCA
-                case 1: set_af(m, (a >> 1) | (a << 7), (a & 1) ? FLAG_C : 0); break;   // RRCA
-                case 2: set_af(m, (a << 1) | c, (a >> 7) ? FLAG_C : 0); break;         // RLA
-                case 3: set_af(m, (a >> 1) | (c << 7), (a & 1) ? FLAG_C : 0); break;   // RRA
-                case 4: {                                                              // DAA
-                    uint32_t corr = ((f & FLAG_H) ? 0x06 : 0) | ((f & FLAG_C) ? 0x60 : 0), t = a;
-                    if (f & FLAG_N) {
-                        t -= corr;
-                    } else {
-                        if ((t & 0x0F) > 9) corr |= 0x06;
-                        if (t > 0x99) corr |= 0x60;
-                        t += corr;
-                    }
-                    t &= 0xFF;
-                    set_af(m, t, (f & FLAG_N) | (t == 0 ? FLAG_Z : 0) | ((corr & 0x60) ? FLAG_C : 0));
-                    break;
-                }
-                case 5: set_af(m, ~a, f | FLAG_N | FLAG_H); break;                     // CPL
-                case 6: set_f(m, (f & FLAG_Z) | FLAG_C); break;                        // SCF
-                default: set_f(m, (f & FLAG_Z) | ((f & FLAG_C) ^ FLAG_C)); break;      // CCF
-                }
-                NEXT(1);
-                cycles = 4;
-                break;
-            }
-            }
-        } else {  // x == 3
-            bool illegal = false;
-            switch (z) {
-            case 0:
-                if (y < 4) {  // RET cc
-                    if (rn) { m.pc = rv; m.sp = (m.sp + 2) & 0xFFFF; cycles = 20; }
-                    else { NEXT(1); cycles = 8; }
-                } else if (y == 4) { WRITE8(0xFF00 + imm8, reg_a(m)); NEXT(2); cycles = 12; }
-                else if (y == 6) { set_a(m, rv); NEXT(2); cycles = 12; }
-                else {  // ADD SP,e / LD HL,SP+e
-                    uint32_t sp = m.sp;
-                    uint32_t nf = (((sp & 0xF) + (imm8 & 0xF)) > 0xF ? FLAG_H : 0) | (((sp & 0xFF) + imm8) > 0xFF ? FLAG_C : 0);
-                    uint32_t t = (sp + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;
-                    set_f(m, nf);
-                    NEXT(2);
-                    if (y == 5) { m.sp = t; cycles = 16; }
-                    else { set_hl(m, t); cycles = 12; }
-                }
-                break;
-            case 1:
-                if (q == 0) {  // POP
-                    m.sp = (m.sp + 2) & 0xFFFF;
-                    if (p == 3) set_af(m, rv >> 8, rv & 0xF0);
-                    else set_reg_pair(m, p, rv);
-                    NEXT(1);
-                    cycles = 12;
-                } else if (p < 2) {  // RET / RETI
-                    if (p == 1) m.ime = 1;
-                    m.pc = rv;
-                    m.sp = (m.sp + 2) & 0xFFFF;
-                    cycles = 16;
-                } else if (p == 2) { m.pc = hl; cycles = 4; }
-                else { m.sp = hl; NEXT(1); cycles = 8; }
-                break;
-            case 2:
-                if (y < 4) {
-                    if (condition(m, y)) { m.pc = imm16; cycles = 16; }
-                    else { NEXT(3); cycles = 12; }
-                } else if (y == 4) { WRITE8(0xFF00 + (m.bcde & 0xFF), reg_a(m)); NEXT(1); cycles = 8; }
-                else if (y == 5) { WRITE8(imm16, reg_a(m)); NEXT(3); cycles = 16; }
-                else if (y == 6) { set_a(m, rv); NEXT(1); cycles = 8; }
-                else { set_a(m, rv); NEXT(3); cycles = 16; }
-                break;
-            case 3:
-                if (y == 0) { m.pc = imm16; cycles = 16; }
-                else if (y == 6) { m.ime = 0; NEXT(1); cycles = 4; }
-                else if (y == 7) { m.ime = 1; NEXT(1); cycles = 4; }  // PyBoy: EI takes effect immediately
-                else illegal = true;  // (y == 1 is the CB prefix, handled above)
-                break;
-            case 4:
-                if (y < 4) {
-                    NEXT(3);
-                    if (condition(m, y)) { PUSH16(m.pc); m.pc = imm16; cycles = 24; }
-                    else cycles = 12;
-                } else illegal = true;
-                break;
-            case 5:
-                if (q == 0) {  // PUSH
-                    PUSH16((p == 3) ? ((reg_a(m) << 8) | reg_f(m)) : reg_pair(m, p));
-                    NEXT(1);
-                    cycles = 16;
-                } else if (p == 0) {  // CALL nn
-                    NEXT(3);
-                    PUSH16(m.pc);
-                    m.pc = imm16;
-                    cycles = 24;
-                } else illegal = true;
-                break;
-            case 6:
-                alu8(m, y, imm8);
-                NEXT(2);
-                cycles = 8;
-                break;
-            default:  // RST
-                NEXT(1);
-                PUSH16(m.pc);
-                m.pc = y * 8;
-                cycles = 16;
-                break;
-            }
-            if (illegal) {  // PyBoy raises; we latch a fault and behave as a 1-byte 4-cycle NOP
-                m.fault = 1;
-                NEXT(1);
-                cycles = 4;
-            }
-        }
-#undef NEXT
-        m.n_instr++;
-        m.iq = 0;
-    }
-    // ---- write phase
-    for (uint32_t i = 0; i < wn; i++) bus_write_full(m, i ? w1a : w0a, i ? w1v : w0v);
-#undef PUSH16
-#undef WRITE8
-    return cycles;
 }

@@ -1,8 +1,12 @@
 // gb_kernels.cuh -- emulation kernels: the 24-frame step, state scatter/gather, bus access.
 #pragma once
+#include "gb_cpu.cuh"
 #include "gb_device.cuh"
 
 #define STEP_THREADS 128
+#ifndef STEP_MIN_BLOCKS
+#define STEP_MIN_BLOCKS 1
+#endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
 // (Right Left Up Down A B Select Start, the bit order of PyBoy's Interaction nibbles)
@@ -24,7 +28,7 @@ struct RunParams {
 // outer body performs the mode change (scanline parameters, rendering, LY/STAT/interrupt flags).  All
 // envs see the same number of LCD events per frame, so the warp re-converges 442 times a frame and
 // the scanline renderer runs with all 32 lanes active.
-__global__ void __launch_bounds__(STEP_THREADS) k_run_frames(RunParams p) {
+__global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(RunParams p) {
     __shared__ uint32_t s_line[FB_LINE_WORDS * STEP_THREADS];
     __shared__ uint32_t s_keys[10 * STEP_THREADS];
     const int tid = threadIdx.x;
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_run_frames(RunParams p) {
         while (!done) {
             bool event;
             do {
-                uint32_t cycles = cpu_step(m);
+                uint32_t cycles = cpu_step(m, p.d.rom_dec);
                 if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
                     int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
                     int c = a < b ? a : b;

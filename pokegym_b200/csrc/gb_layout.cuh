@@ -67,6 +67,7 @@ struct DevArrays {
     uint32_t *lp;    // [tiles][LP_WORDS][32]
     uint32_t *regs;  // [tiles][R_WORDS][32]
     const uint8_t *rom;
+    const uint2 *rom_dec;  // pre-decoded ROM: one 8-byte instruction descriptor per ROM offset (gb_predecode.h)
     uint32_t rom_banks;
     int n_envs;
     int n_tiles;

@@ -258,7 +258,7 @@ extern "C" int gbenv_destroy(gbenv *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &t : h->templates) cudaFree(t.d_image);
-    cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree((void *)h->d.rom);
+    cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree((void *)h->d.rom); cudaFree((void *)h->d.rom_dec);
     cudaFree(h->w.state); cudaFree(h->w.visited); cudaFree(h->w.counts_map);
     cudaFree(h->d_counters); cudaFree(h->d_stage_image); cudaFree(h->d_stage_buf); cudaFree(h->d_info_rows);
     cudaFree(h->d_env_ids); cudaFree(h->d_mask); cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_reward);
@@ -302,6 +302,9 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     uint8_t *d_rom = nullptr;
     ALLOC(d_rom, rom_len + 16);  // padded: the instruction fetch reads two aligned words
     h->d.rom = d_rom;
+    uint2 *d_rom_dec = nullptr;
+    ALLOC(d_rom_dec, rom_len * sizeof(uint2));
+    h->d.rom_dec = d_rom_dec;
     h->d.rom_banks = (uint32_t)(rom_len / 0x4000);
     h->d.n_envs = n_envs;
     h->d.n_tiles = h->n_tiles;
@@ -317,11 +320,12 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     }
     h->w.slots = slots;
     {   // envs per warp: the interpreter is latency-bound, so spread a small batch over many warps.
-        // Aim for >= 16 warps per SM; GBENV_LANES overrides.
+        // About 16 warps per SM; GBENV_LANES / gbenv_set_lanes_per_warp override.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id);
-        int lanes = 32;
-        while (lanes > 1 && (n_envs + lanes - 1) / lanes < sms * 16) lanes >>= 1;
+        // measured on B200 (profiles/): 4,096 envs run best at 2-4 envs per warp, >= 32k envs at 32
+        int lanes = 2;
+        while (lanes < 32 && (n_envs + lanes - 1) / lanes > sms * 16) lanes <<= 1;
         if (const char *ev = getenv("GBENV_LANES")) {
             int v = atoi(ev);
             if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
@@ -344,6 +348,13 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     for (auto &slot : h->ev)
         for (auto &e : slot) CK(cudaEventCreate(&e));
     CK(cudaMemcpy(d_rom, rom_host, rom_len, cudaMemcpyHostToDevice));
+    {   // decode the shared ROM once (gb_predecode.h): 8 bytes per ROM offset, L2-resident
+        uint32_t base[512];
+        pd_build_base(base);
+        CK(cudaMemcpyToSymbol(c_base_desc, base, sizeof(base)));
+        k_predecode_rom<<<(unsigned)((rom_len + 255) / 256), 256, 0, h->stream>>>(d_rom, (uint32_t)rom_len, d_rom_dec);
+        CK(cudaGetLastError());
+    }
     k_wrap_init<<<(n_envs + 127) / 128, 128, 0, h->stream>>>(h->w, n_envs);
     CK(cudaGetLastError());
     std::vector<uint32_t> img;
