@@ -75,26 +75,30 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
 #define WRITE8(addr, val) do { w0a = (addr) & 0xFFFF; w0v = (val); wn = 1; } while (0)
 
     bool execute = true;
-    if (!m.iq) {
-        uint32_t pending = m.iflag & m.ie & 0x1F;
-        if (pending) {  // CPU.handle_interrupt for the highest-priority pending source
-            uint32_t bit = pending & (0u - pending);
-            if (m.halted) m.pc = (m.pc + 1) & 0xFFFF;
-            if (m.ime) {
-                m.iflag ^= bit;
-                PUSH16(m.pc);
-                m.pc = 0x40 + 8 * (31 - __clz(bit));
-                m.ime = 0;
+    // One cheap predicate guards everything that is not plain execution (pending interrupt, HALT, PyBoy's
+    // interrupt_queued latch): on the hot path this is two logic ops and a never-taken branch.
+    if (m.halted | m.iq | (m.iflag & m.ie & 0x1F)) {
+        if (!m.iq) {
+            uint32_t pending = m.iflag & m.ie & 0x1F;
+            if (pending) {  // CPU.handle_interrupt for the highest-priority pending source
+                uint32_t bit = pending & (0u - pending);
+                if (m.halted) m.pc = (m.pc + 1) & 0xFFFF;
+                if (m.ime) {
+                    m.iflag ^= bit;
+                    PUSH16(m.pc);
+                    m.pc = 0x40 + 8 * (31 - __clz(bit));
+                    m.ime = 0;
+                }
+                m.iq = 1;
+                m.halted = 0;
+                execute = false;
             }
-            m.iq = 1;
+        } else if (m.halted) {  // debugger-only path in PyBoy: halted with a queued interrupt
             m.halted = 0;
-            execute = false;
+            m.pc = (m.pc + 1) & 0xFFFF;
         }
-    } else if (m.halted) {  // debugger-only path in PyBoy: halted with a queued interrupt
-        m.halted = 0;
-        m.pc = (m.pc + 1) & 0xFFFF;
+        if (execute && m.halted) return 4;
     }
-    if (execute && m.halted) return 4;
     if (execute) {
         const uint32_t pc = m.pc;
         // ---- fetch: one descriptor load; byte-wise decode only for RAM code and bank-straddling instructions

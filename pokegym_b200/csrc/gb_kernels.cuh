@@ -63,10 +63,9 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
                     int c = a < b ? a : b;
                     cycles = c < 0 ? 0 : (uint32_t)c;
                 }
-                m.n_cycles += cycles;
                 timer_tick(m, cycles);
                 m.clock += cycles;
-                event = (m.lcdc & 0x80) ? (m.clock >= m.target) : (m.clock >= FRAME_CYCLES);
+                event = m.clock >= ((m.lcdc & 0x80) ? m.target : FRAME_CYCLES);
             } while (!event);
             lcd_event(m, line, keys, ls);
             done = m.frame_done;
