@@ -591,6 +591,9 @@ static int fetch_and_execute(GbCore *g) {
     uint16_t pc = g->PC;
     uint8_t op = gb_read(g, pc);
     uint8_t n8 = gb_read(g, (uint16_t)(pc + 1));
+#ifdef GB_OPCODE_HOOK /* optional instruction-mix profiling (tools only) */
+    GB_OPCODE_HOOK(op, n8);
+#endif
     uint16_t n16 = (uint16_t)(n8 | (gb_read(g, (uint16_t)(pc + 2)) << 8));
     int s8 = (int)((n8 ^ 0x80) - 0x80);
     int x = op >> 6, y = (op >> 3) & 7, z = op & 7, p = y >> 1, q = y & 1;

@@ -33,7 +33,7 @@ __global__ void k_predecode_rom(const uint8_t *rom, uint32_t rom_len, uint2 *out
 }
 
 // cold half of a data read: VRAM, cart RAM, OAM, IO array, IO registers -- inputs by value
-__device__ __noinline__ uint32_t rd8_slow(uint32_t a, const uint8_t *memb, const uint8_t *cramb, uint32_t ram, uint32_t lcd0, uint32_t lcd1,
+__device__ __noinline__ uint32_t rd8_slow(uint32_t a, const uint8_t *memb, const uint8_t *cramb, uint32_t ram, uint32_t lcd0, uint32_t scroll,
                                           uint32_t pal_ie, uint32_t tim, uint32_t iflag) {
     if (a < 0xA000) {
         uint32_t i = MEM_VRAM + (a - 0x8000);
@@ -45,7 +45,7 @@ __device__ __noinline__ uint32_t rd8_slow(uint32_t a, const uint8_t *memb, const
         return cramb[((i >> 2) << 7) | (i & 3)];
     }
     if (a >= 0xFF00) {
-        uint32_t r = io_reg_read(a, lcd0, lcd1, pal_ie, tim, iflag);
+        uint32_t r = io_reg_read(a, lcd0, scroll, pal_ie, tim, iflag);
         if (r != IO_NOT_A_REGISTER) return r;
     }
     uint32_t i = MEM_HI + (a - 0xFE00);
@@ -56,9 +56,8 @@ __device__ __forceinline__ uint32_t rd8(Machine &m, uint32_t a) {  // Motherboar
     if (a - 0xC000u < 0x3E00u) return mem_rd(m, MEM_WRAM + (a & 0x1FFF));      // WRAM and its echo
     if (a >= 0xFF80 && a != 0xFFFF) return mem_rd(m, MEM_HI + (a - 0xFE00));    // HRAM
     if (a < 0x8000) return __ldg(m.rom + (a < 0x4000 ? a : a + m.rom_off));     // ROM data tables
-    return rd8_slow(a, m.memb, m.cramb, m.ram_en | (m.rambank << 8), m.lcdc | (m.stat << 8) | (m.ly << 16) | (m.lyc << 24),
-                    m.scy | (m.scx << 8) | (m.wy << 16) | (m.wx << 24), m.bgp | (m.obp0 << 8) | (m.obp1 << 16) | (m.ie << 24),
-                    ((m.div + (m.divc >> 8)) & 0xFF) | (m.tima << 8) | (m.tma << 16) | (m.tac << 24), m.iflag);
+    return rd8_slow(a, m.memb, m.cramb, m.ram_en | (m.rambank << 8), m.lcdc | (m.stat << 8) | (m.ly << 16) | (m.lyc << 24), m.scroll,
+                    m.pal | (m.ie << 24), ((m.div + (m.divc >> 8)) & 0xFF) | m.tmr, m.iflag);
 }
 
 __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict__ rom_dec) {

@@ -28,16 +28,31 @@
 
 #define FRAME_CYCLES 70224u
 
+#define M_SCX(m) ((m).scroll & 0xFF)
+#define M_SCY(m) (((m).scroll >> 8) & 0xFF)
+#define M_WX(m) (((m).scroll >> 16) & 0xFF)
+#define M_WY(m) ((m).scroll >> 24)
+#define M_BGP(m) ((m).pal & 0xFF)
+#define M_OBP0(m) (((m).pal >> 8) & 0xFF)
+#define M_OBP1(m) (((m).pal >> 16) & 0xFF)
+#define M_TIMA(m) (((m).tmr >> 8) & 0xFF)
+#define M_TMA(m) (((m).tmr >> 16) & 0xFF)
+#define M_TAC(m) ((m).tmr >> 24)
+
 struct Machine {
     // SM83 registers: C|B<<8|E<<16|D<<24 and L|H<<8|A<<16|F<<24 (pairs are native little-endian halves)
     uint32_t bcde, hlaf, sp, pc;
     uint32_t ime, halted, stopped, iq, fault, ie, iflag;
     // LCD
-    uint32_t lcdc, stat, ly, lyc, scy, scx, wy, wx, bgp, obp0, obp1;
+    // hot LCD registers unpacked; the rest stay packed the way the out-of-line IO / renderer paths consume them
+    uint32_t lcdc, stat, ly, lyc;
+    uint32_t scroll;  // SCX | SCY<<8 | WX<<16 | WY<<24  (the order of PyBoy's per-scanline parameter record)
+    uint32_t pal;     // BGP | OBP0<<8 | OBP1<<16
     uint32_t stat_mode, next_mode, disable_renderer, frame_done;
     uint32_t clock, target;
     // timer
-    uint32_t div, tima, tma, tac, divc, timac;
+    uint32_t div, divc, timac;
+    uint32_t tmr;  // TIMA<<8 | TMA<<16 | TAC<<24
     // MBC3
     uint32_t rombank, rambank, ram_en, memorymodel, rom_off;
     // joypad + renderer bookkeeping
@@ -86,14 +101,14 @@ __device__ inline void machine_load(Machine &m, const DevArrays &d, int tile, in
     w = r[R_LCD0 * 32];
     m.lcdc = w & 0xFF; m.stat = (w >> 8) & 0xFF; m.ly = (w >> 16) & 0xFF; m.lyc = w >> 24;
     w = r[R_LCD1 * 32];
-    m.scy = w & 0xFF; m.scx = (w >> 8) & 0xFF; m.wy = (w >> 16) & 0xFF; m.wx = w >> 24;
+    m.scroll = ((w & 0x00FF00FFu) << 8) | ((w >> 8) & 0x00FF00FFu);  // R_LCD1 holds SCY SCX WY WX
     w = r[R_LCD2 * 32];
-    m.bgp = w & 0xFF; m.obp0 = (w >> 8) & 0xFF; m.obp1 = (w >> 16) & 0xFF;
+    m.pal = w & 0xFFFFFFu;
     m.stat_mode = (w >> 24) & 3; m.next_mode = (w >> 26) & 3; m.disable_renderer = (w >> 28) & 1; m.frame_done = (w >> 29) & 1;
     m.clock = r[R_CLOCK * 32];
     m.target = r[R_TARGET * 32];
     w = r[R_TIMER * 32];
-    m.div = w & 0xFF; m.tima = (w >> 8) & 0xFF; m.tma = (w >> 16) & 0xFF; m.tac = w >> 24;
+    m.div = w & 0xFF; m.tmr = w & 0xFFFFFF00u;
     m.divc = r[R_DIVC * 32];
     m.timac = r[R_TIMAC * 32];
     w = r[R_MBC * 32];
@@ -119,11 +134,11 @@ __device__ inline void machine_store(Machine &m, const DevArrays &d, int tile, i
     r[R_SPPC * 32] = (m.sp & 0xFFFF) | (m.pc << 16);
     r[R_INT * 32] = m.ime | (m.halted << 1) | (m.stopped << 2) | (m.iq << 3) | (m.fault << 4) | (m.ie << 8) | (m.iflag << 16);
     r[R_LCD0 * 32] = m.lcdc | (m.stat << 8) | (m.ly << 16) | (m.lyc << 24);
-    r[R_LCD1 * 32] = m.scy | (m.scx << 8) | (m.wy << 16) | (m.wx << 24);
-    r[R_LCD2 * 32] = m.bgp | (m.obp0 << 8) | (m.obp1 << 16) | ((m.stat_mode | (m.next_mode << 2) | (m.disable_renderer << 4) | (m.frame_done << 5)) << 24);
+    r[R_LCD1 * 32] = ((m.scroll & 0x00FF00FFu) << 8) | ((m.scroll >> 8) & 0x00FF00FFu);
+    r[R_LCD2 * 32] = m.pal | ((m.stat_mode | (m.next_mode << 2) | (m.disable_renderer << 4) | (m.frame_done << 5)) << 24);
     r[R_CLOCK * 32] = m.clock;
     r[R_TARGET * 32] = m.target;
-    r[R_TIMER * 32] = m.div | (m.tima << 8) | (m.tma << 16) | (m.tac << 24);
+    r[R_TIMER * 32] = m.div | m.tmr;
     r[R_DIVC * 32] = m.divc;
     r[R_TIMAC * 32] = m.timac;
     r[R_MBC * 32] = m.rombank | (m.rambank << 8) | (m.ram_en << 16) | (m.memorymodel << 24);
@@ -223,7 +238,8 @@ __device__ __forceinline__ uint32_t apply_palette16(uint32_t idx16, uint32_t pal
 // scratch in shared memory (stride `ls` words), `keys` its 10-entry sprite sort scratch.
 __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint32_t *keys, uint32_t ls) {
     const uint32_t lcdc = m.lcdc;
-    const int wx = (int)m.wx - 7, wy = (int)m.wy;
+    const int wx = (int)M_WX(m) - 7, wy = (int)M_WY(m);
+    const uint32_t scx = M_SCX(m), scy = M_SCY(m), bgp = M_BGP(m);
     const bool win_line = (lcdc & 0x20) && wy <= (int)y && wx < 160;
     if (win_line) m.ly_window += 1;
     const uint32_t tds = lcdc & 0x10;
@@ -233,11 +249,11 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
     if (wstart > 0) {
         if (lcdc & 0x01) {
             const uint32_t map_base = (lcdc & 0x08) ? 0x1C00u : 0x1800u;
-            const uint32_t row = map_base + ((((y + m.scy) >> 3) << 5) & 0x3FFu);
-            const uint32_t fine_y = (y + m.scy) & 7;
-            uint32_t col = m.scx >> 3;
+            const uint32_t row = map_base + ((((y + scy) >> 3) << 5) & 0x3FFu);
+            const uint32_t fine_y = (y + scy) & 7;
+            uint32_t col = scx >> 3;
             uint64_t acc = 0;
-            int nbits = -(int)((m.scx & 7) * 2);  // drop the leftmost (scx & 7) pixels of the first tile
+            int nbits = -(int)((scx & 7) * 2);  // drop the leftmost (scx & 7) pixels of the first tile
             uint32_t out = 0;
             const uint32_t nwords = ((uint32_t)wstart + 15) >> 4;
             while (out < nwords) {
@@ -245,7 +261,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
                 col++;
                 if (!tds) t = (t ^ 0x80) + 128;
                 uint32_t rowdata = vram_rd16(m, MEM_VRAM + t * 16 + fine_y * 2);
-                uint32_t px = apply_palette16(tile_row_indices(rowdata & 0xFF, rowdata >> 8), m.bgp);
+                uint32_t px = apply_palette16(tile_row_indices(rowdata & 0xFF, rowdata >> 8), bgp);
                 if (nbits < 0) {
                     acc = (uint64_t)(px >> (uint32_t)(-nbits));
                     nbits += 16;
@@ -261,7 +277,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
                 }
             }
         } else {
-            uint32_t fill = pal_shade(m.bgp, 0) * 0x55555555u;
+            uint32_t fill = pal_shade(bgp, 0) * 0x55555555u;
             for (uint32_t k = 0; k < ((uint32_t)wstart + 15) >> 4; k++) line[k * ls] = fill;
         }
     }
@@ -283,7 +299,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
             col++;
             if (!tds) t = (t ^ 0x80) + 128;
             uint32_t rowdata = vram_rd16(m, MEM_VRAM + t * 16 + fine_y * 2);
-            uint32_t px = apply_palette16(tile_row_indices(rowdata & 0xFF, rowdata >> 8), m.bgp);
+            uint32_t px = apply_palette16(tile_row_indices(rowdata & 0xFF, rowdata >> 8), bgp);
             if (first_tile) {
                 px >>= (first & 7) * 2;
                 acc |= (uint64_t)px << lead;
@@ -339,7 +355,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
             }
             uint32_t idx16 = tile_row_indices(b1, b2);
             uint32_t opaque = (idx16 | (idx16 >> 1)) & 0x5555u;  // 1 per non-transparent pixel (even bit)
-            uint32_t shades = apply_palette16(idx16, (attr & 0x10) ? m.obp1 : m.obp0);
+            uint32_t shades = apply_palette16(idx16, (attr & 0x10) ? M_OBP1(m) : M_OBP0(m));
             // clip to the screen
             if (sx < 0) {
                 uint32_t cut = (uint32_t)(-sx) * 2;
@@ -371,13 +387,11 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
 
 // Out-of-line entry points of the renderer: inputs by value, so the caller's Machine stays in registers
 // and the (large) renderer body is kept out of the interpreter's hot loop.
-__device__ __noinline__ int render_line_out(uint8_t *memb, uint32_t *fb, uint32_t a /* lcdc | scy<<8 | scx<<16 | bgp<<24 */,
-                                            uint32_t b /* wy | wx<<8 | obp0<<16 | obp1<<24 */, int ly_window, uint32_t y, uint32_t *line,
-                                            uint32_t *keys, uint32_t ls) {
+__device__ __noinline__ int render_line_out(uint8_t *memb, uint32_t *fb, uint32_t lcdc, uint32_t scroll, uint32_t pal, int ly_window, uint32_t y,
+                                            uint32_t *line, uint32_t *keys, uint32_t ls) {
     Machine r;
     r.memb = memb; r.fb = fb;
-    r.lcdc = a & 0xFF; r.scy = (a >> 8) & 0xFF; r.scx = (a >> 16) & 0xFF; r.bgp = a >> 24;
-    r.wy = b & 0xFF; r.wx = (b >> 8) & 0xFF; r.obp0 = (b >> 16) & 0xFF; r.obp1 = b >> 24;
+    r.lcdc = lcdc; r.scroll = scroll; r.pal = pal;
     r.ly_window = ly_window;
     render_line(r, y, line, keys, ls);
     return r.ly_window;
@@ -388,7 +402,7 @@ __device__ __noinline__ void fill_framebuffer(uint32_t *fb, uint32_t fill) {
 }
 
 __device__ __forceinline__ void lcd_blank_screen(Machine &m) {
-    uint32_t shade = pal_shade(m.bgp, 0);
+    uint32_t shade = pal_shade(M_BGP(m), 0);
     if (m.blank_shade == shade) return;  // already uniformly this shade: the refill would be a no-op
     fill_framebuffer(m.fb, shade * 0x55555555u);
     m.blank_shade = shade;
@@ -420,13 +434,12 @@ __device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uin
             m.target += 206;
             if (m.ly < 144) {
                 if (m.lp_dirty) {  // Renderer._scanlineparameters[y]
-                    uint2 v = make_uint2(m.scx | (m.scy << 8) | (m.wx << 16) | (m.wy << 24), m.lcdc);
+                    uint2 v = make_uint2(m.scroll, m.lcdc);
                     m.lp[m.ly << 5] = v;
                     m.lp_dirty--;
                 }
                 if (!m.disable_renderer) {
-                    m.ly_window = render_line_out(m.memb, m.fb, m.lcdc | (m.scy << 8) | (m.scx << 16) | (m.bgp << 24),
-                                                  m.wy | (m.wx << 8) | (m.obp0 << 16) | (m.obp1 << 24), m.ly_window, m.ly, line, keys, ls);
+                    m.ly_window = render_line_out(m.memb, m.fb, m.lcdc, m.scroll, m.pal, m.ly_window, m.ly, line, keys, ls);
                     m.blank_shade = 0xFF;
                 }
             }
@@ -461,24 +474,24 @@ __device__ __forceinline__ uint32_t timer_divider(uint32_t tac) {
 
 __device__ __forceinline__ void timer_tick(Machine &m, uint32_t cycles) {
     m.divc += cycles;  // DIV = div + (divc >> 8), materialised on read / store
-    if (m.tac & 4) {
+    if (m.tmr & 0x04000000u) {  // TAC bit 2: timer enabled
         m.timac += cycles;
-        uint32_t dv = timer_divider(m.tac);
+        uint32_t dv = timer_divider(M_TAC(m));
         if (m.timac >= dv) {
             m.timac -= dv;
-            if (m.tima == 0xFF) {
-                m.tima = m.tma;
+            if (M_TIMA(m) == 0xFF) {
+                m.tmr = (m.tmr & 0xFFFF00FFu) | (M_TMA(m) << 8);
                 m.iflag |= IRQ_TIMER;
             } else {
-                m.tima += 1;
+                m.tmr += 0x100;
             }
         }
     }
 }
 
 __device__ __forceinline__ int timer_cycles_to_interrupt(const Machine &m) {
-    if (!(m.tac & 4)) return 1 << 16;
-    return (int)((0x100 - m.tima) * timer_divider(m.tac)) - (int)m.timac;
+    if (!(m.tmr & 0x04000000u)) return 1 << 16;
+    return (int)((0x100 - M_TIMA(m)) * timer_divider(M_TAC(m))) - (int)m.timac;
 }
 
 // --------------------------------------------------------------------------------------------- bus
@@ -490,7 +503,8 @@ __device__ __forceinline__ int timer_cycles_to_interrupt(const Machine &m) {
 
 #define IO_NOT_A_REGISTER 0x100u
 // value of an IO register modelled outside the IO array, or IO_NOT_A_REGISTER
-__device__ __noinline__ uint32_t io_reg_read(uint32_t a, uint32_t lcd0, uint32_t lcd1, uint32_t pal_ie, uint32_t tim, uint32_t iflag) {
+__device__ __noinline__ uint32_t io_reg_read(uint32_t a, uint32_t lcd0 /* LCDC STAT LY LYC */, uint32_t scroll /* SCX SCY WX WY */,
+                                             uint32_t pal_ie /* BGP OBP0 OBP1 IE */, uint32_t tim /* DIV TIMA TMA TAC */, uint32_t iflag) {
     switch (a) {
     case 0xFF04: return tim & 0xFF;
     case 0xFF05: return (tim >> 8) & 0xFF;
@@ -499,16 +513,16 @@ __device__ __noinline__ uint32_t io_reg_read(uint32_t a, uint32_t lcd0, uint32_t
     case 0xFF0F: return iflag;
     case 0xFF40: return lcd0 & 0xFF;
     case 0xFF41: return (lcd0 >> 8) & 0xFF;
-    case 0xFF42: return lcd1 & 0xFF;
-    case 0xFF43: return (lcd1 >> 8) & 0xFF;
+    case 0xFF42: return (scroll >> 8) & 0xFF;
+    case 0xFF43: return scroll & 0xFF;
     case 0xFF44: return (lcd0 >> 16) & 0xFF;
     case 0xFF45: return lcd0 >> 24;
     case 0xFF46: return 0;
     case 0xFF47: return pal_ie & 0xFF;
     case 0xFF48: return (pal_ie >> 8) & 0xFF;
     case 0xFF49: return (pal_ie >> 16) & 0xFF;
-    case 0xFF4A: return (lcd1 >> 16) & 0xFF;
-    case 0xFF4B: return lcd1 >> 24;
+    case 0xFF4A: return scroll >> 24;
+    case 0xFF4B: return (scroll >> 16) & 0xFF;
     case 0xFFFF: return pal_ie >> 24;
     default: return (a >= 0xFF10 && a < 0xFF40) ? 0u : IO_NOT_A_REGISTER;  // sound disabled (pokegym default): reads 0
     }
@@ -525,9 +539,8 @@ __device__ __forceinline__ uint32_t bus_read_full(Machine &m, uint32_t a) {  // 
         return m.cramb[((i >> 2) << 7) | (i & 3)];
     }
     if (a >= 0xFF00) {
-        uint32_t r = io_reg_read(a, m.lcdc | (m.stat << 8) | (m.ly << 16) | (m.lyc << 24), m.scy | (m.scx << 8) | (m.wy << 16) | (m.wx << 24),
-                                 m.bgp | (m.obp0 << 8) | (m.obp1 << 16) | (m.ie << 24),
-                                 ((m.div + (m.divc >> 8)) & 0xFF) | (m.tima << 8) | (m.tma << 16) | (m.tac << 24), m.iflag);
+        uint32_t r = io_reg_read(a, m.lcdc | (m.stat << 8) | (m.ly << 16) | (m.lyc << 24), m.scroll, m.pal | (m.ie << 24),
+                                 ((m.div + (m.divc >> 8)) & 0xFF) | m.tmr, m.iflag);
         if (r != IO_NOT_A_REGISTER) return r;
     }
     return mem_rd(m, MEM_HI + (a - 0xFE00));  // OAM, 0xFEA0-0xFEFF, plain IO array bytes
@@ -567,14 +580,14 @@ __device__ __noinline__ void bus_write_rare(Machine *mp, uint32_t a, uint32_t v)
     switch (a) {
     case 0xFF00: mem_wr(m, MEM_HI + 0x100, joypad_pull(m, v)); break;
     case 0xFF04: m.div = 0; m.divc = 0; m.timac = 0; break;
-    case 0xFF05: m.tima = v; break;
-    case 0xFF06: m.tma = v; break;
-    case 0xFF07: m.tac = v & 7; break;
+    case 0xFF05: m.tmr = (m.tmr & 0xFFFF00FFu) | (v << 8); break;
+    case 0xFF06: m.tmr = (m.tmr & 0xFF00FFFFu) | (v << 16); break;
+    case 0xFF07: m.tmr = (m.tmr & 0x00FFFFFFu) | ((v & 7) << 24); break;
     case 0xFF0F: m.iflag = v; break;
     case 0xFF40: lcd_set_lcdc(m, v); break;
     case 0xFF41: m.stat = (m.stat & 0x87) | (v & 0x78); break;
-    case 0xFF42: if (v != m.scy) m.lp_dirty = 144; m.scy = v; break;
-    case 0xFF43: if (v != m.scx) m.lp_dirty = 144; m.scx = v; break;
+    case 0xFF42: if (v != M_SCY(m)) m.lp_dirty = 144; m.scroll = (m.scroll & 0xFFFF00FFu) | (v << 8); break;
+    case 0xFF43: if (v != M_SCX(m)) m.lp_dirty = 144; m.scroll = (m.scroll & 0xFFFFFF00u) | v; break;
     case 0xFF44: m.ly = v; m.lp_dirty = 144; break;  // PyBoy lets LY be written
     case 0xFF45: m.lyc = v; break;
     case 0xFF46: {  // Motherboard.transfer_DMA: instantaneous copy of 0xA0 bytes to OAM
@@ -588,11 +601,11 @@ __device__ __noinline__ void bus_write_rare(Machine *mp, uint32_t a, uint32_t v)
         }
         break;
     }
-    case 0xFF47: m.bgp = v; break;
-    case 0xFF48: m.obp0 = v; break;
-    case 0xFF49: m.obp1 = v; break;
-    case 0xFF4A: if (v != m.wy) m.lp_dirty = 144; m.wy = v; break;
-    case 0xFF4B: if (v != m.wx) m.lp_dirty = 144; m.wx = v; break;
+    case 0xFF47: m.pal = (m.pal & 0xFFFF00u) | v; break;
+    case 0xFF48: m.pal = (m.pal & 0xFF00FFu) | (v << 8); break;
+    case 0xFF49: m.pal = (m.pal & 0x00FFFFu) | (v << 16); break;
+    case 0xFF4A: if (v != M_WY(m)) m.lp_dirty = 144; m.scroll = (m.scroll & 0x00FFFFFFu) | (v << 24); break;
+    case 0xFF4B: if (v != M_WX(m)) m.lp_dirty = 144; m.scroll = (m.scroll & 0xFF00FFFFu) | (v << 16); break;
     case 0xFFFF: m.ie = v; break;
     default:
         if (a >= 0xFF10 && a < 0xFF40) break;  // sound disabled: writes dropped

@@ -171,14 +171,14 @@ __global__ void k_debug_render_frame(DevArrays d, int env) {
     if (threadIdx.x || blockIdx.x) return;
     Machine m;
     machine_load(m, d, env >> 5, env & 31);
-    const uint32_t scx = m.scx, scy = m.scy, wx = m.wx, wy = m.wy, lcdc = m.lcdc;
+    const uint32_t scroll = m.scroll, lcdc = m.lcdc;
     m.ly_window = -1;
     for (uint32_t y = 0; y < 144; y++) {
         uint2 v = m.lp[y << 5];
-        m.scx = v.x & 0xFF; m.scy = (v.x >> 8) & 0xFF; m.wx = (v.x >> 16) & 0xFF; m.wy = v.x >> 24;
+        m.scroll = v.x;
         m.lcdc = (lcdc & ~0x10u) | (v.y & 0x10);
         render_line(m, y, s_line, s_keys, 1);
     }
-    m.scx = scx; m.scy = scy; m.wx = wx; m.wy = wy; m.lcdc = lcdc;
+    m.scroll = scroll; m.lcdc = lcdc;
     machine_store(m, d, env >> 5, env & 31);
 }
