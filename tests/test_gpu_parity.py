@@ -123,3 +123,48 @@ def test_memory_api_and_inputs(cuda_lib, oracle_lib, roms):
         assert np.array_equal(gpu.read_mem(2, addr, cnt), cpu.read_mem(2, addr, cnt)), hex(addr)
     assert np.array_equal(gpu.screen(2), cpu.screen(2))
     _assert_same_states(gpu, cpu, range(n), "memory api")
+
+
+def test_readme_config_72_envs_long_run(cuda_lib, oracle_lib, roms):
+    """BASELINE.json config 2 shape: 72 envs (the README training config), random actions, full Environment.step,
+    bit-exact RAM / framebuffer / reward / obs versus 72 oracle instances.  2,000 steps by default
+    (GBENV_LONG_STEPS=10000 for the full 10k-step run)."""
+    import hashlib
+    import os
+
+    import torch
+
+    n, steps = 72, int(os.environ.get("GBENV_LONG_STEPS", "2000"))
+    gpu, cpu = _pair(cuda_lib, oracle_lib, roms("pokelike"), n)
+    gpu.tick(60, True)
+    cpu.tick(60, True)
+    og = torch.zeros((n, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
+    rg = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dg = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    oc = np.zeros((n, _capi.OBS_BYTES), dtype=np.uint8)
+    rc = np.zeros(n)
+    dc = np.zeros(n, dtype=np.uint8)
+    gpu.reset(og, max_episode_steps=700)
+    cpu.reset(oc, max_episode_steps=700)
+    gen = torch.Generator().manual_seed(0)
+    actions = torch.randint(0, 8, (steps, n), generator=gen, dtype=torch.uint8)  # SURVEY.md 8d action generator
+    rsum = np.zeros(n)
+    for s in range(steps):
+        a = actions[s].numpy()
+        gpu.step(actions[s].cuda(), og, rg, dg)
+        cpu.step(a, oc, rc, dc)
+        r = rg.cpu().numpy()
+        assert np.array_equal(r, rc), f"reward differs at step {s}"
+        rsum += np.abs(r)
+        if s % 50 == 49 or s == steps - 1:
+            assert np.array_equal(og.cpu().numpy(), oc), f"obs differs at step {s}"
+            assert np.array_equal(dg.cpu().numpy(), dc)
+        if dc.any():  # the vectoriser resets an env on the call after done
+            gpu.reset(og, mask=dc, max_episode_steps=700)
+            cpu.reset(oc, mask=dc, max_episode_steps=700)
+        if s % 250 == 249 or s == steps - 1:
+            for e in (0, 17, 35, 71):
+                assert hashlib.sha256(gpu.save_state(e)).digest() == hashlib.sha256(cpu.save_state(e)).digest(), (s, e)
+    assert (rsum > 0).all()
+    assert gpu.counters().faults == 0
+    _assert_same_states(gpu, cpu, range(n), "end of long run")
