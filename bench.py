@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--rom", default="pokelike")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--also-envs", type=int, default=32768, help="extra single-GPU leg at this env count (0 = skip); reported under 'large_batch'")
+    ap.add_argument("--also-steps", type=int, default=12)
     return ap.parse_args()
 
 
@@ -322,6 +324,35 @@ def main():
         "clocks": clocks,
         "faults": int(c1.faults),
     }
+    if world == 1 and args.also_envs and args.also_envs != E:
+        # the interpreter is issue/latency bound, so throughput keeps growing with the number of resident envs:
+        # report the north_star's ">= 32k envs per B200" point next to the headline 4,096-env configuration
+        try:
+            h.close()
+            del rollout
+            torch.cuda.empty_cache()
+            E2 = args.also_envs
+            h2 = _capi.Handle(lib, E2, rom, device_id=local_rank)
+            h2.tick(60, True)
+            ro2 = torch.zeros((4, E2, _capi.OBS_BYTES), dtype=torch.uint8, device=dev)
+            rw2 = torch.zeros(E2, dtype=torch.float64, device=dev)
+            dn2 = torch.zeros(E2, dtype=torch.uint8, device=dev)
+            act2 = torch.randint(0, 8, (3 + args.also_steps, E2), generator=gen, device=dev, dtype=torch.uint8)
+            h2.reset(ro2[0])
+            for i in range(3):
+                h2.step(act2[i], ro2[i % 4], rw2, dn2)
+            torch.cuda.synchronize()
+            ev0.record()
+            for i in range(3, 3 + args.also_steps):
+                h2.step(act2[i], ro2[i % 4], rw2, dn2)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms2 = ev0.elapsed_time(ev1)
+            line["large_batch"] = {"envs_per_gpu": E2, "value": E2 * args.also_steps / (ms2 / 1000.0), "unit": "env-steps/s", "steps": args.also_steps,
+                                   "ms_per_step": ms2 / args.also_steps, "faults": int(h2.counters().faults)}
+            h2.close()
+        except Exception as e:
+            line["large_batch"] = {"error": str(e)}
     try:
         v, cores, sample = oracle_env_steps_per_s(rom, args.cpu_baseline_seconds)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}

@@ -218,17 +218,19 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
             }
             break;
         }
+        case H_ROT_A: {  // RLCA RRCA RLA RRA: Z N H cleared, C = bit shifted out
+            const uint32_t a = reg_a(m), cin = (reg_f(m) >> 4) & 1, left = !(y & 1), thru = y >> 1;
+            const uint32_t out = left ? (a >> 7) : (a & 1), in = thru ? cin : out;
+            set_af(m, left ? ((a << 1) | in) : ((a >> 1) | (in << 7)), out ? FLAG_C : 0);
+            break;
+        }
         default: {  // H_RARE
-            const uint32_t op = PD_OP(dx), a = reg_a(m), f = reg_f(m), c = (f >> 4) & 1;
+            const uint32_t op = PD_OP(dx), a = reg_a(m), f = reg_f(m);
             switch (op) {
             case 0x76: m.halted = 1; next_pc = pc; break;              // HALT: PC stays on the HALT byte
             case 0x10: next_pc = (pc + 2) & 0xFFFF; break;             // STOP skips a byte
             case 0xF3: m.ime = 0; break;
             case 0xFB: m.ime = 1; break;  // PyBoy: EI takes effect immediately
-            case 0x07: set_af(m, (a << 1) | (a >> 7), (a >> 7) ? FLAG_C : 0); break;  // RLCA
-            case 0x0F: set_af(m, (a >> 1) | (a << 7), (a & 1) ? FLAG_C : 0); break;   // RRCA
-            case 0x17: set_af(m, (a << 1) | c, (a >> 7) ? FLAG_C : 0); break;         // RLA
-            case 0x1F: set_af(m, (a >> 1) | (c << 7), (a & 1) ? FLAG_C : 0); break;   // RRA
             case 0x27: {                                                              // DAA
                 uint32_t corr = ((f & FLAG_H) ? 0x06 : 0) | ((f & FLAG_C) ? 0x60 : 0), t = a;
                 if (f & FLAG_N) {

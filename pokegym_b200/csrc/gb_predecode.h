@@ -25,7 +25,7 @@ enum {
     H_NOP, H_LD_R_R, H_LD_R_HL, H_LD_HL_R, H_LD_R_N, H_LD_HL_N, H_LD_A_RP, H_LD_RP_A,
     H_LDH_N_A, H_LDH_A_N, H_LD_C_A, H_LD_A_C, H_LD_NN_A, H_LD_A_NN,
     H_ALU_R, H_ALU_HL, H_ALU_N, H_INCDEC_R, H_INCDEC_HL, H_LD_RP_NN, H_INCDEC_RP, H_ADD_HL,
-    H_JR, H_JP, H_CALL, H_RET, H_RETI, H_RST, H_PUSH, H_POP, H_CB_R, H_CB_HL, H_RARE,
+    H_JR, H_JP, H_CALL, H_RET, H_RETI, H_RST, H_PUSH, H_POP, H_CB_R, H_CB_HL, H_ROT_A, H_RARE,
     H__COUNT
 };
 
@@ -56,7 +56,9 @@ static inline void pd_build_base(uint32_t *t) {
             case 4:
             case 5: d = y == 6 ? pd_make(H_INCDEC_HL, y, z, 1, 12, 12, op) : pd_make(H_INCDEC_R, y, z, 1, 4, 4, op); break;
             case 6: d = y == 6 ? pd_make(H_LD_HL_N, y, z, 2, 12, 12, op) : pd_make(H_LD_R_N, y, z, 2, 8, 8, op); break;
-            default: break;  // RLCA .. CCF: rare
+            default:
+                if (y < 4) d = pd_make(H_ROT_A, y, z, 1, 4, 4, op);  // RLCA RRCA RLA RRA
+                break;  // DAA CPL SCF CCF: rare
             }
         } else {
             switch (z) {
