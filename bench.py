@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--rom", default="pokelike")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
-    ap.add_argument("--also-envs", type=int, default=32768, help="extra single-GPU leg at this env count (0 = skip); reported under 'large_batch'")
+    ap.add_argument("--also-envs", type=int, default=-1,
+                    help="extra single-GPU leg at this env count, reported under 'large_batch' (0 = skip; -1 = one full wave: SMs x 20 warps x 32 envs)")
     ap.add_argument("--also-steps", type=int, default=12)
     return ap.parse_args()
 
@@ -324,6 +325,8 @@ def main():
         "clocks": clocks,
         "faults": int(c1.faults),
     }
+    if args.also_envs < 0:
+        args.also_envs = torch.cuda.get_device_properties(dev).multi_processor_count * 20 * 32  # 94,720 on a 148-SM B200
     if world == 1 and args.also_envs and args.also_envs != E:
         # the interpreter is issue/latency bound, so throughput keeps growing with the number of resident envs:
         # report the north_star's ">= 32k envs per B200" point next to the headline 4,096-env configuration

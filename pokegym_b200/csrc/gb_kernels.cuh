@@ -5,7 +5,7 @@
 
 #define STEP_THREADS 128
 #ifndef STEP_MIN_BLOCKS
-#define STEP_MIN_BLOCKS 1
+#define STEP_MIN_BLOCKS 5
 #endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
