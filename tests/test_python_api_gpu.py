@@ -87,3 +87,60 @@ def _loaded(oracle_lib, rom, blob):
     o = np.zeros((1, _capi.OBS_BYTES), np.uint8)
     h.reset(o)
     return h.save_state(0)
+
+
+def test_error_paths_and_limits(cuda_lib, roms, monkeypatch):
+    import torch
+
+    from pokegym_b200 import _capi
+
+    rom = roms("pokelike")
+    with pytest.raises(_capi.GbEnvError):
+        _capi.Handle(cuda_lib, 0, rom)  # no envs
+    with pytest.raises(_capi.GbEnvError):
+        _capi.Handle(cuda_lib, 4, rom[:1000])  # not a ROM image
+    with pytest.raises(_capi.GbEnvError):
+        _capi.Handle(cuda_lib, 4, rom, device_id=99)
+    h = _capi.Handle(cuda_lib, 4, rom)
+    with pytest.raises(_capi.GbEnvError, match="save-state"):
+        h.add_state_template(b"\x09" + bytes(142_609 - 1))  # wrong length
+    bad = bytearray(h.save_state(0))
+    bad[9125] = 0x77  # a framebuffer word PyBoy never produces
+    with pytest.raises(_capi.GbEnvError, match="framebuffer"):
+        h.add_state_template(bytes(bad))
+    with pytest.raises(_capi.GbEnvError):
+        h.load_template(5)
+    with pytest.raises(_capi.GbEnvError):
+        h.read_mem(9, 0xC000, 1)
+    with pytest.raises(_capi.GbEnvError):
+        h.set_lanes_per_warp(3)
+    obs = torch.zeros((4, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
+    with pytest.raises(_capi.GbEnvError):
+        h.reset(obs, obs_stride=100)
+    # results do not depend on the lanes-per-warp tuning knob
+    states = []
+    for lanes in (1, 8, 32):
+        g = _capi.Handle(cuda_lib, 40, rom)
+        g.set_lanes_per_warp(lanes)
+        g.tick(20, True)
+        a = torch.arange(40, dtype=torch.uint8, device="cuda") % 8
+        for _ in range(3):
+            g.run_action(a)
+        states.append([g.save_state(e) for e in (0, 13, 39)])
+    assert states[0] == states[1] == states[2]
+    # visited-bitmap slots: an env that walks through more maps than it has slots raises the fault counter
+    monkeypatch.setenv("GBENV_VISITED_SLOTS", "2")
+    monkeypatch.setenv("GBENV_COUNTS_MAP", "0")
+    s = _capi.Handle(cuda_lib, 2, rom)
+    s.tick(30, True)
+    rew = torch.zeros(2, dtype=torch.float64, device="cuda")
+    done = torch.zeros(2, dtype=torch.uint8, device="cuda")
+    obs2 = torch.zeros((2, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
+    s.reset(obs2)
+    act = torch.zeros(2, dtype=torch.uint8, device="cuda")
+    for m in (1, 2, 3):
+        s.write_mem(1, 0xD35E, [m])  # teleport env 1 to another map
+        s.step(act, obs2, rew, done)
+    assert s.counters().faults == 1
+    with pytest.raises(_capi.GbEnvError, match="exploration map"):
+        s.counts_map(0)
