@@ -100,10 +100,11 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
     }
     if (execute) {
         const uint32_t pc = m.pc;
-        // ---- fetch: one descriptor load; byte-wise decode only for RAM code and bank-straddling instructions
-        uint2 d = make_uint2(H_SLOW, 0);
-        if (pc < 0x8000) d = __ldg(rom_dec + (pc < 0x4000 ? pc : pc + m.rom_off));
-        if (PD_H(d.x) == H_SLOW) {
+        // ---- fetch: one unconditional descriptor load (RAM code reads entry 0 and discards it); byte-wise decode
+        // only for RAM code and bank-straddling instructions
+        const bool in_rom = pc < 0x8000;
+        uint2 d = __ldg(rom_dec + (in_rom ? (pc < 0x4000 ? pc : pc + m.rom_off) : 0u));
+        if (!in_rom || PD_H(d.x) == H_SLOW) {
             uint32_t ins = 0;
             for (uint32_t i = 0; i < 3; i++) ins |= rd8(m, (pc + i) & 0xFFFF) << (8 * i);
             d = pd_decode_bytes(ins, pc);

@@ -58,12 +58,16 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
             bool event;
             do {
                 uint32_t cycles = cpu_step(m, p.d.rom_dec);
-                if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
-                    int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
-                    int c = a < b ? a : b;
-                    cycles = c < 0 ? 0 : (uint32_t)c;
+                if (m.halted | (m.tmr & 0x04000000u)) {  // rare: HALT fast-forward and/or a running TIMA
+                    if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
+                        int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
+                        int c = a < b ? a : b;
+                        cycles = c < 0 ? 0 : (uint32_t)c;
+                    }
+                    timer_tick(m, cycles);
+                } else {
+                    m.divc += cycles;  // Timer.tick with the timer stopped: only DIV advances (kept lazily)
                 }
-                timer_tick(m, cycles);
                 m.clock += cycles;
                 event = m.clock >= ((m.lcdc & 0x80) ? m.target : FRAME_CYCLES);
             } while (!event);
