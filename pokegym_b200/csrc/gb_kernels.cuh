@@ -55,22 +55,46 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
         bool done = m.frame_done;
         m.frame_done = 0;
         while (!done) {
-            bool event;
-            do {
-                uint32_t cycles = cpu_step(m, p.d.rom_dec);
-                if (m.halted | (m.tmr & 0x04000000u)) {  // rare: HALT fast-forward and/or a running TIMA
-                    if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
-                        int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
-                        int c = a < b ? a : b;
-                        cycles = c < 0 ? 0 : (uint32_t)c;
+            if (m.halted && !(m.iq | (m.iflag & m.ie & 0x1F) | (m.tmr & 0x04000000u)) && (m.lcdc & 0x80)) {
+                // Quiet HALT (nothing pending, TIMA stopped): CPU.tick is a no-op and Motherboard.tick jumps
+                // straight to the next LCD mode change, so the interpreter is not entered at all.
+                if (m.disable_renderer && m.stat_mode == 0 && m.next_mode == 2 && m.ly < 143 && !(m.stat & 0x78)) {
+                    // In HBlank with no STAT interrupt source armed and rendering off, the mode 2/3/0 events of
+                    // the remaining visible lines change only LY, STAT, the clocks and the saved scanline
+                    // parameters: run them in closed form up to HBlank of line 143 (the VBlank event that
+                    // follows raises the interrupt that ends the HALT).
+                    const uint32_t k = 143 - m.ly;
+                    for (uint32_t y = m.ly + 1; m.lp_dirty && y <= 143; y++) {
+                        m.lp[y << 5] = make_uint2(m.scroll, m.lcdc);
+                        m.lp_dirty--;
                     }
-                    timer_tick(m, cycles);
-                } else {
-                    m.divc += cycles;  // Timer.tick with the timer stopped: only DIV advances (kept lazily)
+                    m.ly = 143;
+                    m.stat = (m.stat & 0xF8) | (m.lyc == 143 ? 0x04 : 0);
+                    m.next_mode = 1;
+                    m.target += 456 * k;
+                    const int adv = (int)(m.target - 206 - m.clock);  // clock of the last skipped mode change
+                    if (adv > 0) { m.divc += adv; m.clock += adv; }
                 }
-                m.clock += cycles;
-                event = m.clock >= ((m.lcdc & 0x80) ? m.target : FRAME_CYCLES);
-            } while (!event);
+                const int a = (int)(m.target - m.clock);
+                if (a > 0) { m.divc += a; m.clock += a; }
+            } else {
+                bool event;
+                do {
+                    uint32_t cycles = cpu_step(m, p.d.rom_dec);
+                    if (m.halted | (m.tmr & 0x04000000u)) {  // rare: HALT fast-forward and/or a running TIMA
+                        if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
+                            int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
+                            int c = a < b ? a : b;
+                            cycles = c < 0 ? 0 : (uint32_t)c;
+                        }
+                        timer_tick(m, cycles);
+                    } else {
+                        m.divc += cycles;  // Timer.tick with the timer stopped: only DIV advances (kept lazily)
+                    }
+                    m.clock += cycles;
+                    event = m.clock >= ((m.lcdc & 0x80) ? m.target : FRAME_CYCLES);
+                } while (!event);
+            }
             lcd_event(m, line, keys, ls);
             done = m.frame_done;
             m.frame_done = 0;
