@@ -6,7 +6,7 @@ observation per env-step), BASELINE.json's metric.
 
 * one process per GPU; for N > 1 the driver launches this file under torchrun (RANK / LOCAL_RANK /
   WORLD_SIZE / MASTER_* from the environment) and every rank owns E envs (weak scaling, SURVEY.md 8e);
-  the only collective is the NCCL all-reduce of the 64-double episode-info vector once per 32-step rollout.
+  the only collective is the NCCL all-reduce of the 72-double episode-info vector once per 32-step rollout.
 * `value`   : whole-job env-steps/s with actions already resident in HBM and observations written into a
               device rollout tensor u8[32, E, 72*80*4]; CUDA-event timed, max over ranks.
 * `e2e`     : the same metric through the host-buffer C-ABI call gbenv_step_host (pinned host memory;
@@ -232,7 +232,7 @@ def main():
     rollout = torch.zeros((ROLLOUT_T, E, _capi.OBS_BYTES), dtype=torch.uint8, device=dev)
     reward = torch.zeros((ROLLOUT_T, E), dtype=torch.float64, device=dev)
     done = torch.zeros((ROLLOUT_T, E), dtype=torch.uint8, device=dev)
-    info_sum = torch.zeros(64, dtype=torch.float64, device=dev)
+    info_sum = torch.zeros(_capi.INFO_SCALARS, dtype=torch.float64, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     actions = torch.randint(0, 8, (W + K, E), generator=gen, device=dev, dtype=torch.uint8)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GBENV_ABI_VERSION 1
+#define GBENV_ABI_VERSION 2 /* 2: info row widened from 64 to 72 doubles (per-item bag rewards) */
 
 #define GBENV_STATE_BYTES 142610 /* PyBoy v9 save-state length              */
 #define GBENV_OBS_H 72           /* environment.py:154-166: (144//2, 160//2, 4) uint8       */
@@ -41,7 +41,7 @@ extern "C" {
 #define GBENV_SCREEN_W 160
 #define GBENV_NUM_ACTIONS 8 /* pyboy_binding.ACTIONS :40  Down Left Right Up A B Start Select */
 #define GBENV_ACT_FREQ 24   /* pyboy_binding.run_action_on_emulator :72 frame_skip=24         */
-#define GBENV_INFO_SCALARS 64
+#define GBENV_INFO_SCALARS 72
 
 enum {
     GBENV_OK = 0,

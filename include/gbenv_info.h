@@ -3,7 +3,7 @@
  *
  * Numeric entries of the reference's `info["stats"]` and `info["reward"]` dicts
  * (/root/reference/pokegym/environment.py:1621-1703), refreshed by every gbenv_step.  Multi-GPU runs
- * sum these rows over envs on each rank and all-reduce the 64-double vector over NCCL
+ * sum these rows over envs on each rank and all-reduce the GBENV_INFO_SCALARS-double vector over NCCL
  * (SURVEY.md section 8e); slot 0 carries the env count so means can be formed afterwards.
  */
 #ifndef GBENV_INFO_H
@@ -69,13 +69,18 @@ enum {
     GBI_R_ABS,
     GBI_SEEN_COORDS,
     GBI_DONE,
+    GBI_R_LEMONADE, /* has_<item>_in_bag_reward: 0 or 20, sticky for the env lifetime (environment.py:1358-1372) */
+    GBI_R_SILPH_SCOPE,
+    GBI_R_LIFT_KEY,
+    GBI_R_POKEDOLL,
+    GBI_R_BICYCLE,
     GBI__END
 };
 
 #if defined(__cplusplus)
-static_assert(GBI__END <= 64, "info row overflows GBENV_INFO_SCALARS");
+static_assert(GBI__END <= 72, "info row overflows GBENV_INFO_SCALARS");
 #else
-typedef char gbi_fits_in_row[(GBI__END <= 64) ? 1 : -1];
+typedef char gbi_fits_in_row[(GBI__END <= 72) ? 1 : -1];
 #endif
 
 #endif

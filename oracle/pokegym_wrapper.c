@@ -508,6 +508,7 @@ double pg_after_emulation(PgWrapper *w, GbCore *g, int action, uint8_t *obs, int
     I[GBI_R_EXPLORATION] = exploration_reward; I[GBI_R_TREE_DISTANCE] = tree_distance_reward; I[GBI_R_DOJO_OLD] = dojo_reward;
     I[GBI_R_ITEMS] = w->item_reward[0] + w->item_reward[1] + w->item_reward[2] + w->item_reward[3] + w->item_reward[4];
     I[GBI_R_USED_CUT] = cut_rew; I[GBI_R_ABS] = reward_abs; I[GBI_SEEN_COORDS] = w->n_seen_coords; I[GBI_DONE] = *done;
+    for (int k = 0; k < 5; k++) I[GBI_R_LEMONADE + k] = w->item_reward[k];
     render(w, g, obs); /* :1812 */
     return reward;
 }

@@ -23,7 +23,7 @@ extern "C" {
 
 #define PG_MAPS 248
 #define PG_CUT_COORDS_MAX 512
-#define PG_INFO_SCALARS 64
+#define PG_INFO_SCALARS 72
 
 typedef struct PgCutCoord {
     int32_t x, y, map;

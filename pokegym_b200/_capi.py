@@ -17,7 +17,8 @@ import numpy as np
 STATE_BYTES = 142_610
 OBS_H, OBS_W, OBS_C = 72, 80, 4
 OBS_BYTES = OBS_H * OBS_W * OBS_C
-INFO_SCALARS = 64
+INFO_SCALARS = 72
+ABI_VERSION = 2
 NUM_ACTIONS = 8
 ACT_FREQ = 24
 
@@ -107,6 +108,8 @@ class GbEnvLib:
             fn.argtypes = argtypes
             fn.restype = restype
             setattr(self, name, fn)
+        if self.abi_version() != ABI_VERSION:  # buffer sizes (info row width) are fixed by the ABI version
+            raise GbEnvError(f"{self.path}: ABI version {self.abi_version()} != {ABI_VERSION} expected by this package; rebuild the library")
 
 
 class Handle:

@@ -12,6 +12,7 @@
 //                 writes uint8[72,80,4] rows straight into the caller's rollout tensor, 320 contiguous
 //                 bytes per env row, with channel 3 cut from the visited bitmap.
 #pragma once
+#include "../../include/gbenv.h"
 #include "../../include/gbenv_info.h"
 #include "gb_device.cuh"
 
@@ -482,8 +483,8 @@ __global__ void __launch_bounds__(128) k_wrap_step(DevArrays d, WrapArrays w, do
     reward[env] = rew;
     done[env] = (uint8_t)dn;
     if (info_rows) {
-        double *I = info_rows + (size_t)env * 64;
-        for (int k = 0; k < 64; k++) I[k] = 0.0;
+        double *I = info_rows + (size_t)env * GBENV_INFO_SCALARS;
+        for (int k = 0; k < GBENV_INFO_SCALARS; k++) I[k] = 0.0;
         I[GBI_COUNT] = 1; I[GBI_STEP] = s.time; I[GBI_X] = sc.c; I[GBI_Y] = sc.r; I[GBI_MAP] = sc.map_n; I[GBI_PCOUNT] = sc.party_size;
         for (uint32_t k = 0; k < 6; k++) I[GBI_LEVEL0 + k] = RAM(m, 0xD18C + 44 * k);
         I[GBI_LEVELS_SUM] = sc.level_sum; I[GBI_COORD_SUM] = (double)s.coord_sum;
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(128) k_wrap_step(DevArrays d, WrapArrays w, do
         I[GBI_R_TREE_DISTANCE] = sc.tree_distance_reward; I[GBI_R_DOJO_OLD] = sc.dojo_reward;
         I[GBI_R_ITEMS] = s.item_reward[0] + s.item_reward[1] + s.item_reward[2] + s.item_reward[3] + s.item_reward[4];
         I[GBI_R_USED_CUT] = sc.cut_rew; I[GBI_R_ABS] = sc.reward_abs; I[GBI_SEEN_COORDS] = s.n_seen_coords; I[GBI_DONE] = dn;
+        for (int k = 0; k < 5; k++) I[GBI_R_LEMONADE + k] = s.item_reward[k];
     }
     // the wrapper only writes plain WRAM bytes (straight to HBM): no register write-back is needed
 }
@@ -628,12 +630,12 @@ __global__ void __launch_bounds__(256) k_wrap_obs(DevArrays d, WrapArrays w, con
     }
 }
 
-// sum of the info rows over envs -> 64 doubles (the vector multi-GPU runs all-reduce over NCCL)
+// sum of the info rows over envs -> GBENV_INFO_SCALARS doubles (the vector multi-GPU runs all-reduce over NCCL)
 __global__ void k_reduce_info(const double *rows, int n_envs, double *sum) {
     __shared__ double s[256];
     const int k = blockIdx.x;  // one block per info slot
     double acc = 0.0;
-    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) acc += rows[(size_t)e * 64 + k];
+    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) acc += rows[(size_t)e * GBENV_INFO_SCALARS + k];
     s[threadIdx.x] = acc;
     __syncthreads();
     for (int st = blockDim.x / 2; st > 0; st >>= 1) {

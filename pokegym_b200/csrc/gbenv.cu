@@ -340,7 +340,7 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     ALLOC(h->d_counters, 8 * sizeof(unsigned long long));
     ALLOC(h->d_stage_image, IMG_WORDS * sizeof(uint32_t));
     ALLOC(h->d_stage_buf, 0x10000);
-    ALLOC(h->d_info_rows, (size_t)n_envs * 64 * sizeof(double));
+    ALLOC(h->d_info_rows, (size_t)n_envs * GBENV_INFO_SCALARS * sizeof(double));
     ALLOC(h->d_env_ids, (size_t)n_envs * sizeof(int32_t));
     ALLOC(h->d_mask, (size_t)n_envs);
 #undef ALLOC
@@ -636,14 +636,14 @@ extern "C" int gbenv_reset_host(gbenv *h, const uint8_t *mask, int max_episode_s
 extern "C" int gbenv_get_info(gbenv *h, double *info_dev, void *stream) {
     if (!h || !info_dev) return fail(h, GBENV_E_ARG, "gbenv_get_info: bad argument");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(info_dev, h->d_info_rows, (size_t)h->n * 64 * sizeof(double), cudaMemcpyDeviceToDevice, pick(h, stream)));
+    CK(cudaMemcpyAsync(info_dev, h->d_info_rows, (size_t)h->n * GBENV_INFO_SCALARS * sizeof(double), cudaMemcpyDeviceToDevice, pick(h, stream)));
     return GBENV_OK;
 }
 
 extern "C" int gbenv_reduce_info(gbenv *h, double *sum_dev, void *stream) {
     if (!h || !sum_dev) return fail(h, GBENV_E_ARG, "gbenv_reduce_info: bad argument");
     CK(cudaSetDevice(h->device));
-    k_reduce_info<<<64, 256, 0, pick(h, stream)>>>(h->d_info_rows, h->n, sum_dev);
+    k_reduce_info<<<GBENV_INFO_SCALARS, 256, 0, pick(h, stream)>>>(h->d_info_rows, h->n, sum_dev);
     h->launches++;
     CK(cudaGetLastError());
     return GBENV_OK;

@@ -1,7 +1,7 @@
 """Multi-GPU plumbing: envs shard across ranks with no data-path collective.
 
 One process per GPU (torchrun); rank r owns a contiguous slice of the global env index range; the only
-exchange is a sum all-reduce of the 64-double episode-info vector, once per rollout, over NCCL on GPUs
+exchange is a sum all-reduce of the 72-double episode-info vector, once per rollout, over NCCL on GPUs
 (gloo in the CPU tests).  Timing of multi-rank runs is the max over ranks.
 """
 from __future__ import annotations

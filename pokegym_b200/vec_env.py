@@ -18,7 +18,7 @@ from typing import Iterable, Optional, Sequence, Union
 import numpy as np
 
 from . import _capi
-from .info import INFO_NAMES, info_row_to_dict
+from .info import INFO_NAMES, build_info, info_row_to_dict  # noqa: F401
 
 try:  # gymnasium is not installed in this image; use it when it is
     from gymnasium.spaces import Box, Discrete  # type: ignore
@@ -169,6 +169,17 @@ class VecEnvironment:
         self.handle.reduce_info(out, stream=self._stream())
         return out
 
+    def full_info(self, env: int = 0) -> dict:
+        """The reference's complete info dict for one env (environment.py:1621-1810): scalar row + the 130 named
+        event flags (read from the env's WRAM) + its counts_map.  Rare path (episode end / every 10,000 steps)."""
+        row = self.info()[env].cpu().numpy()
+        wram = self.handle.read_mem(env, 0xD700, 0x200)  # every event flag lives in 0xD7B1..0xD838
+        try:
+            cm = self.handle.counts_map(env).astype(np.float64)
+        except _capi.GbEnvError:  # counts maps disabled for very large batches (GBENV_COUNTS_MAP=0)
+            cm = None
+        return build_info(row, lambda a: int(wram[a - 0xD700]), counts_map=cm, reward_scale=self.reward_scale)
+
     def save_state(self, env: int = 0) -> bytes:
         return self.handle.save_state(env)
 
@@ -205,11 +216,7 @@ class Environment:
         d = bool(done[0].item())
         info = {}
         if d or self.time % 10000 == 0:  # environment.py:1621
-            info = info_row_to_dict(self.vec.info()[0].cpu().numpy())
-            try:
-                info["pokemon_exploration_map"] = self.vec.handle.counts_map(0).astype(np.float64)
-            except _capi.GbEnvError:
-                pass
+            info = self.vec.full_info(0)
         self._last_obs = obs[0].cpu().numpy()
         return self._last_obs, float(reward[0].item()), d, d, info
 

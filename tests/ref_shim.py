@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import contextlib
 import io
+import copy
 import os
 import sys
 import tempfile
@@ -220,7 +221,7 @@ def run_reference_episode(rom: bytes, oracle_lib, state_blob: bytes, actions, ma
         out["obs"].append(np.array(obs, copy=True))
         out["states"].append(pyboy.handle.save_state(0))
         out["writes"].append(list(pyboy.mem_writes))
-        out.setdefault("infos", []).append(info)
+        out.setdefault("infos", []).append(copy.deepcopy(info) if info else info)  # counts_map is mutated by later steps
     out["env"] = env
     os.unlink(path)
     return out

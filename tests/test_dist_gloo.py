@@ -40,7 +40,7 @@ def _worker(rank, world, port, n_total, steps, lib_path, q):
     actions = np.random.default_rng(0).integers(0, 8, (steps, n_total)).astype(np.uint8)  # global action table, sliced per rank
     for s in range(steps):
         h.step(np.ascontiguousarray(actions[s, lo:hi]), obs, rew, done)
-    local = np.zeros(64)
+    local = np.zeros(_capi.INFO_SCALARS)
     h.reduce_info(local)
     total = torch.from_numpy(local.copy())
     all_reduce_info(total)
@@ -77,7 +77,7 @@ def test_two_rank_sharded_run_matches_single_process(built):
     actions = np.random.default_rng(0).integers(0, 8, (steps, n_total)).astype(np.uint8)
     for s in range(steps):
         h.step(actions[s], obs, rew, done)
-    ref = np.zeros(64)
+    ref = np.zeros(_capi.INFO_SCALARS)
     h.reduce_info(ref)
     assert np.array_equal(res[0][2], res[1][2]), "ranks disagree after the all-reduce"
     assert np.allclose(res[0][2], ref, rtol=0, atol=1e-9), "sharded sum differs from the single-process sum"

@@ -82,8 +82,8 @@ def test_step_reward_obs_match_oracle(cuda_lib, oracle_lib, roms):
             assert np.array_equal(og.cpu().numpy(), oc)
     assert total > 0
     _assert_same_states(gpu, cpu, range(0, n, 7), "after steps")
-    ig = torch.zeros((n, 64), dtype=torch.float64, device="cuda")
-    ic = np.zeros((n, 64))
+    ig = torch.zeros((n, _capi.INFO_SCALARS), dtype=torch.float64, device="cuda")
+    ic = np.zeros((n, _capi.INFO_SCALARS))
     gpu.get_info(ig)
     cpu.get_info(ic)
     gpu.sync()

@@ -27,6 +27,12 @@ def test_environment_facade_matches_pokegym_signatures(cuda_lib, oracle_lib, rom
         assert np.array_equal(obs, o.reshape(72, 80, 4)) and np.array_equal(env.render(), obs)
         assert bool(info) == (s == 4)
     assert info["stats"]["step"] == 5 and "pokemon_exploration_map" in info and info["pokemon_exploration_map"].shape == (444, 436)
+    # the complete reference layout (environment.py:1621-1810): 11 top-level sections, 130 named event flags
+    assert list(info) == ["pokemon_exploration_map", "stats", "reward", "detailed_rewards_silph_co", "detailed_rewards_dojo", "detailed_rewards_hideout",
+                          "detailed_rewards_poke_tower", "detailed_rewards_gyms", "silph_co_events_aggregate", "dojo_events_aggregate",
+                          "hideout_events_aggregate", "poke_tower_events_aggregate", "gym_events"]
+    n_flags = sum(len(info[k]) for k in info if k.endswith("_aggregate")) + sum(len(v) for v in info["gym_events"].values())
+    assert n_flags == 130 and info["reward"]["delta"] == rew
     env.close()
 
 

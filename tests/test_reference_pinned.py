@@ -5,6 +5,7 @@ import pytest
 
 from conftest import REFERENCE, reference_states
 from pokegym_b200 import _capi
+from pokegym_b200.info import build_info
 from pokegym_b200.state_file import diff_states, parse_state, serialize_state
 
 pytestmark = [pytest.mark.reference, pytest.mark.skipif(not REFERENCE.exists(), reason="reference tree not mounted")]
@@ -44,6 +45,22 @@ def test_v7_state_loads(oracle_lib, roms):
     assert st.cpu["PC"] == parse_state(p.read_bytes()).cpu["PC"]
 
 
+def _assert_info_equal(ref, mine, path="info"):
+    """Recursive comparison of the reference's info dict with build_info's (same keys, same order, same numbers)."""
+    if isinstance(ref, dict):
+        assert isinstance(mine, dict) and list(ref) == list(mine), (path, list(ref), list(mine) if isinstance(mine, dict) else mine)
+        for k in ref:
+            _assert_info_equal(ref[k], mine[k], f"{path}[{k!r}]")
+    elif isinstance(ref, set):  # stats["maps_explored"]: the reference's later duplicate key stores np.sum(set) == the set itself
+        assert len(ref) == mine, (path, ref, mine)
+    elif isinstance(ref, np.ndarray) and ref.ndim:
+        assert np.array_equal(ref, np.asarray(mine)), path
+    elif isinstance(ref, (list, tuple)):
+        assert [float(x) for x in ref] == [float(x) for x in mine], (path, ref, mine)
+    else:
+        assert abs(float(ref) - float(mine)) <= 1e-9 * max(1.0, abs(float(ref))), (path, ref, mine)
+
+
 def _compare_with_reference(oracle_lib, rom, start_blob, actions, max_episode_steps, reset_at):
     import ref_shim
 
@@ -57,6 +74,7 @@ def _compare_with_reference(oracle_lib, rom, start_blob, actions, max_episode_st
     assert np.array_equal(obs.reshape(72, 80, 4), ref["reset_obs"][0])
     assert o.save_state(0) == ref["reset_state"][0]
     k = 1
+    n_infos = 0
     for i, a in enumerate(actions):
         if i in reset_at:
             o.reset(obs, max_episode_steps=max_episode_steps)
@@ -68,7 +86,14 @@ def _compare_with_reference(oracle_lib, rom, start_blob, actions, max_episode_st
         assert bool(done[0]) == ref["dones"][i]
         assert np.array_equal(obs.reshape(72, 80, 4), ref["obs"][i]), i
         assert o.save_state(0) == ref["states"][i], (i, diff_states(ref["states"][i], o.save_state(0)))
-    return ref, o
+        if ref["infos"][i]:  # emitted when done or time % 10000 == 0 (environment.py:1620)
+            row = np.zeros((1, _capi.INFO_SCALARS))
+            o.get_info(row)
+            mine = build_info(row[0], lambda a: int(o.read_mem(0, a, 1)[0]), counts_map=o.counts_map(0))
+            _assert_info_equal(ref["infos"][i], mine)
+            n_infos += 1
+    assert n_infos == sum(1 for x in ref["infos"] if x)
+    return ref, o, n_infos
 
 
 def test_wrapper_matches_unmodified_reference_on_synthetic_game(oracle_lib, roms):
@@ -76,13 +101,9 @@ def test_wrapper_matches_unmodified_reference_on_synthetic_game(oracle_lib, roms
     h = _capi.Handle(oracle_lib, 1, rom)
     h.tick(60, True)
     actions = np.random.default_rng(3).integers(0, 8, 500)
-    ref, o = _compare_with_reference(oracle_lib, rom, h.save_state(0), actions, 200, (200, 400))
+    ref, o, n_infos = _compare_with_reference(oracle_lib, rom, h.save_state(0), actions, 200, (200, 400))
     assert np.count_nonzero(ref["rewards"]) > 20
-    # the info dict the reference emits at `done` agrees with the info row
-    infos = [x for x in ref["infos"] if x]
-    assert infos, "no info dict was emitted"
-    row = np.zeros((1, 64))
-    o.get_info(row)
+    assert n_infos >= 2, "the info dict the reference emits at `done` was not compared"
 
 
 @pytest.mark.parametrize("rel", ["current_state/Bulbasaur.state", "bin/checkpoints_battles/bulbasaur/pokemon_ai_14", "bin/checkpoints_bill/pokemon_ai_1005",
@@ -94,7 +115,8 @@ def test_wrapper_matches_reference_from_real_save_states(oracle_lib, roms, rel):
         cands = sorted((REFERENCE / rel).parent.glob("*"))
         p = cands[len(cands) // 2]
     actions = np.random.default_rng(7).integers(0, 8, 60)
-    _compare_with_reference(oracle_lib, roms("pokelike"), p.read_bytes(), actions, 40, (45,))
+    _, _, n_infos = _compare_with_reference(oracle_lib, roms("pokelike"), p.read_bytes(), actions, 40, (45,))
+    assert n_infos >= 1
 
 
 def test_static_tables_match_reference_modules(oracle_lib):
