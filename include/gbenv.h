@@ -63,7 +63,7 @@ const char *gbenv_last_error(const gbenv_t *h);
 int gbenv_num_envs(const gbenv_t *h);
 int gbenv_abi_version(void);
 int gbenv_sync(gbenv_t *h); /* cudaStreamSynchronize on the handle's stream */
-/* Tuning knob: envs carried by each warp of the emulation kernel (power of two, 1..32).  The default is
+/* Tuning knob: envs carried by each warp of the emulation kernel (1..32).  The default is
  * chosen from n_envs and the SM count so that a small batch still fills the GPU with warps.        */
 int gbenv_set_lanes_per_warp(gbenv_t *h, int lanes);
 

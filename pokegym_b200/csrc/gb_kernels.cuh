@@ -18,7 +18,7 @@ struct RunParams {
     int n_frames;
     int render_mode;  // 0: renderer disabled, 1: enabled on every frame, 2: enabled on the last frame only
     int release_frame;  // frame index at which the button is released (8 in the reference)
-    int lanes;          // envs per warp (1..32, power of two): fewer lanes = more warps = more latency hiding
+    int lanes;          // envs per warp (1..32): fewer lanes = more warps = more latency hiding
     unsigned long long *counters;  // [0] instructions, [1] cycles, [2] frames, [3] faults
 };
 

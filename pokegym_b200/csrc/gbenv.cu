@@ -319,16 +319,18 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
         if (v >= 1 && v <= WRAP_MAPS) slots = v;
     }
     h->w.slots = slots;
-    {   // envs per warp: the interpreter is latency-bound, so spread a small batch over many warps.
-        // About 16 warps per SM; GBENV_LANES / gbenv_set_lanes_per_warp override.
+    {   // envs per warp: the interpreter is latency-bound, so spread the batch over as many warps as are resident
+        // at once (one wave: SMs x STEP_MIN_BLOCKS blocks) and no more; GBENV_LANES / gbenv_set_lanes_per_warp override.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id);
-        // measured on B200 (profiles/): 4,096 envs run best at 2-4 envs per warp, >= 32k envs at 32
-        int lanes = 2;
-        while (lanes < 32 && (n_envs + lanes - 1) / lanes > sms * 16) lanes <<= 1;
+        const int resident_warps = sms * STEP_MIN_BLOCKS * (STEP_THREADS / 32);
+        // measured on B200 (tools/quick_bench.sh): the smallest power of two that keeps every warp resident wins; counts
+        // that are not powers of two make warps straddle 32-env tiles (partial 128-byte lines) and lose 3-5 %
+        int lanes = 1;
+        while (lanes < 32 && (n_envs + lanes - 1) / lanes > resident_warps) lanes <<= 1;
         if (const char *ev = getenv("GBENV_LANES")) {
             int v = atoi(ev);
-            if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) lanes = v;
+            if (v >= 1 && v <= 32) lanes = v;
         }
         h->lanes = lanes;
     }
@@ -368,8 +370,7 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
 }
 
 extern "C" int gbenv_set_lanes_per_warp(gbenv *h, int lanes) {
-    if (!h || !(lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
-        return fail(h, GBENV_E_ARG, "gbenv_set_lanes_per_warp: lanes must be a power of two in 1..32");
+    if (!h || lanes < 1 || lanes > 32) return fail(h, GBENV_E_ARG, "gbenv_set_lanes_per_warp: lanes must be in 1..32");
     h->lanes = lanes;
     return GBENV_OK;
 }

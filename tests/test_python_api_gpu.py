@@ -119,13 +119,13 @@ def test_error_paths_and_limits(cuda_lib, roms, monkeypatch):
     with pytest.raises(_capi.GbEnvError):
         h.read_mem(9, 0xC000, 1)
     with pytest.raises(_capi.GbEnvError):
-        h.set_lanes_per_warp(3)
+        h.set_lanes_per_warp(33)
     obs = torch.zeros((4, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
     with pytest.raises(_capi.GbEnvError):
         h.reset(obs, obs_stride=100)
     # results do not depend on the lanes-per-warp tuning knob
     states = []
-    for lanes in (1, 8, 32):
+    for lanes in (1, 3, 12, 32):
         g = _capi.Handle(cuda_lib, 40, rom)
         g.set_lanes_per_warp(lanes)
         g.tick(20, True)
