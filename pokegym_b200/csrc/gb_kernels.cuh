@@ -5,7 +5,9 @@
 
 #define STEP_THREADS 128
 #ifndef STEP_MIN_BLOCKS
+#ifndef STEP_MIN_BLOCKS
 #define STEP_MIN_BLOCKS 5
+#endif
 #endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
