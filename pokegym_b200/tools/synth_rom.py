@@ -1651,10 +1651,227 @@ def build_conformance_rom(seed: int = 7, n_blocks: int = 600) -> bytes:
     return bytes(rom)
 
 
+def build_halt_edge_rom() -> bytes:
+    """HALT / LCD-event edge cases, one scenario per frame, cycling (HRAM 0xA0 = scenario counter):
+
+    0 plain HALT until VBlank                         5 HALT with only the joypad interrupt enabled (sleeps across
+    1 SCX/SCY written just before HALT (scanline          frames until a button edge arrives)
+      parameters pending while halted)                6 LCD switched off, spin, switched on again, HALT
+    2 STAT mode-0 source armed, not enabled in IE     7 HALT with IME=0 and a pending enabled interrupt (wakes at once)
+    3 LYC=100 STAT interrupt wakes the HALT mid-frame 8 window + sprites enabled, WX/WY/LCDC.4 changed before HALT
+    4 LY written mid-frame, then HALT; TIMA running   9 STAT mode-2 + LYC sources armed and enabled; HALT twice
+    Every handler counts into HRAM so missed or extra wake-ups change the state."""
+    rom = bytearray([0xFF]) * ROM_SIZE
+    a = Asm(rom)
+    for v in range(0, 0x40, 8):
+        a.org(v)
+        a.i("RET")
+    for v, name in ((0x40, "VBlank"), (0x48, "StatInt"), (0x50, "TimerInt"), (0x58, "SerialInt"), (0x60, "JoyInt")):
+        a.org(v)
+        a.i("JP nn", name)
+    a.org(0x100)
+    a.i("NOP")
+    a.i("JP nn", "Start")
+    a.org(0x150)
+
+    def handler(name: str, hram: int):
+        a.label(name)
+        a.i("PUSH AF")
+        a.i("LDH A,(n)", hram)
+        a.i("INC A")
+        a.i("LDH (n),A", hram)
+        a.i("LDH A,(n)", 0x44)  # fold LY at wake-up time into a checksum
+        a.i("PUSH HL")
+        a.i("LD HL,nn", 0xC100)
+        a.i("ADD A,(HL)")
+        a.i("RLCA")
+        a.i("LD (HL),A")
+        a.i("POP HL")
+        a.i("POP AF")
+        a.i("RETI")
+
+    handler("VBlank", 0x90)
+    handler("StatInt", 0x91)
+    handler("TimerInt", 0x92)
+    handler("SerialInt", 0x94)
+    handler("JoyInt", 0x93)
+
+    def out(reg: int, v: int):
+        a.i("LD A,n", v)
+        a.i("LDH (n),A", reg)
+
+    a.label("WaitVBlankLine")  # spin (no HALT) until LY == 145
+    a.i("LDH A,(n)", 0x44)
+    a.i("CP n", 145)
+    a.i("JR NZ,e", "WaitVBlankLine")
+    a.i("RET")
+
+    a.label("Start")
+    a.i("DI")
+    a.i("LD SP,nn", 0xDFF0)
+    out(0x0F, 0)
+    out(0xFF, 0x01)
+    out(0x40, 0x91)
+    out(0x47, 0xE4)
+    out(0x48, 0xD0)
+    out(0x49, 0xE0)
+    a.i("XOR A")
+    a.i("LDH (n),A", 0xA0)
+    # a few tiles, a map and two sprites so rendered frames are not blank
+    a.i("LD HL,nn", 0x8000)
+    a.i("LD B,n", 0)
+    a.label("fill_tiles")
+    a.i("LD A,L")
+    a.i("XOR H")
+    a.i("RRCA")
+    a.i("LD (HL+),A")
+    a.i("DEC B")
+    a.i("JR NZ,e", "fill_tiles")
+    a.i("LD HL,nn", 0x9800)
+    a.i("LD B,n", 0)
+    a.label("fill_map")
+    a.i("LD A,L")
+    a.i("AND n", 0x0F)
+    a.i("LD (HL+),A")
+    a.i("DEC B")
+    a.i("JR NZ,e", "fill_map")
+    a.i("LD HL,nn", 0xFE00)
+    for v in (40, 30, 3, 0x00, 90, 100, 5, 0x30):
+        a.i("LD A,n", v)
+        a.i("LD (HL+),A")
+    a.i("EI")
+
+    a.label("MainLoop")
+    a.i("LDH A,(n)", 0xA0)
+    a.i("INC A")
+    a.i("CP n", 10)
+    a.i("JR C,e", "store_scn")
+    a.i("XOR A")
+    a.label("store_scn")
+    a.i("LDH (n),A", 0xA0)
+    for k in range(10):
+        a.i("CP n", k)
+        a.i("JP Z,nn", f"scn{k}")
+    a.i("JP nn", "scn0")
+
+    def end():
+        a.i("JP nn", "MainLoop")
+
+    a.label("scn0")
+    a.i("HALT")
+    end()
+
+    a.label("scn1")
+    a.i("LDH A,(n)", 0x90)
+    a.i("LDH (n),A", 0x43)
+    a.i("CPL")
+    a.i("LDH (n),A", 0x42)
+    a.i("HALT")
+    end()
+
+    a.label("scn2")
+    out(0x41, 0x08)
+    a.i("HALT")
+    out(0x41, 0x00)
+    out(0x0F, 0)
+    end()
+
+    a.label("scn3")
+    out(0x45, 100)
+    out(0x41, 0x40)
+    out(0xFF, 0x03)
+    a.i("HALT")  # woken by LYC=100
+    a.i("HALT")  # then by VBlank
+    out(0x41, 0x00)
+    out(0xFF, 0x01)
+    end()
+
+    a.label("scn4")
+    out(0x06, 0xF0)
+    out(0x07, 0x05)
+    out(0xFF, 0x05)
+    a.i("LDH A,(n)", 0x44)
+    a.i("ADD A,n", 7)
+    a.i("LDH (n),A", 0x44)  # LY is writable in this PyBoy line
+    a.i("HALT")
+    a.i("HALT")
+    out(0x07, 0x00)
+    out(0xFF, 0x01)
+    end()
+
+    a.label("scn5")
+    out(0x00, 0x10)  # select buttons
+    out(0xFF, 0x10)
+    a.i("HALT")  # sleeps until a joypad edge (may span many frames)
+    a.i("LDH A,(n)", 0x00)  # which button: shifts this env's timing relative to its neighbours
+    a.i("AND n", 0x0F)
+    a.i("LD B,A")
+    a.i("INC B")
+    a.i("LD HL,nn", 0xC101)
+    a.label("joy_spin")
+    a.i("INC (HL)")
+    a.i("DEC B")
+    a.i("JR NZ,e", "joy_spin")
+    out(0x00, 0x20)  # select directions for the next time round
+    a.i("LDH A,(n)", 0x00)
+    a.i("LD (nn),A", 0xC102)
+    out(0xFF, 0x01)
+    out(0x0F, 0)
+    end()
+
+    a.label("scn6")
+    a.i("CALL nn", "WaitVBlankLine")
+    out(0x40, 0x11)  # LCD off
+    a.i("LD B,n", 200)
+    a.label("off_spin")
+    a.i("DEC B")
+    a.i("JR NZ,e", "off_spin")
+    out(0x40, 0x91)
+    a.i("HALT")
+    end()
+
+    a.label("scn7")
+    a.i("DI")
+    out(0x0F, 0x01)  # VBlank already pending, IME=0: HALT falls through without dispatch
+    a.i("HALT")
+    a.i("INC B")
+    out(0x0F, 0x00)
+    a.i("EI")
+    a.i("HALT")
+    end()
+
+    a.label("scn8")
+    out(0x4A, 60)
+    out(0x4B, 47)
+    out(0x40, 0xF3)  # window + sprites, unsigned tile data
+    a.i("HALT")
+    out(0x40, 0xE3)  # signed tile data (scanline parameter 5)
+    a.i("HALT")
+    out(0x40, 0x91)
+    end()
+
+    a.label("scn9")
+    out(0x45, 20)
+    out(0x41, 0x60)
+    out(0xFF, 0x03)
+    a.i("HALT")
+    a.i("HALT")
+    out(0x41, 0x00)
+    out(0xFF, 0x01)
+    out(0x0F, 0)
+    a.i("HALT")
+    end()
+
+    a.link()
+    finalize_header(rom, title="HALTEDGE")
+    return bytes(rom)
+
+
 def rom_catalog() -> Dict[str, Tuple]:
     return {
         "pokelike": (build_pokelike_rom, {}),
         "pokelike_timer": (build_pokelike_rom, {"timer": True}),
         "busy": (build_pokelike_rom, {"always_busy": True}),
         "conformance": (build_conformance_rom, {}),
+        "halt_edge": (build_halt_edge_rom, {}),
     }

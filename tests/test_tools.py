@@ -76,3 +76,18 @@ def test_oracle_emulator_is_deterministic_and_actions_matter(oracle_lib, roms):
         outs.append(h.save_state(1))
         assert h.counters().faults == 0
     assert outs[0] == outs[1] and outs[0] != outs[2]
+
+
+def test_halt_edge_rom_cycles_through_every_scenario(oracle_lib, roms):
+    """The HALT/LCD edge-case ROM keeps running on the oracle: every interrupt handler fires, the joypad-only HALT wakes on a button edge, and envs with different actions end in different states."""
+    from pokegym_b200 import _capi
+
+    h = _capi.Handle(oracle_lib, 3, roms("halt_edge"))
+    rng = np.random.default_rng(1)
+    for _ in range(12):
+        h.run_action(rng.integers(0, 8, 3).astype(np.uint8))
+    # one pass over the ten scenarios per env-step: it then sleeps in scenario 5 until the next step's button press
+    vblank, stat, timer, joy = (int(x) for x in h.read_mem(0, 0xFF90, 4))
+    assert int(h.read_mem(0, 0xFFA0, 1)[0]) == 5 and joy >= 8 and vblank >= 100 and stat >= 30 and timer >= 12, (vblank, stat, timer, joy)
+    assert h.counters().faults == 0
+    assert h.save_state(0) != h.save_state(1)
