@@ -4,12 +4,15 @@
 1. ref_wrapper_*.npz -- the UNMODIFIED reference `pokegym.Environment` stepped on the PyBoy shim
    (tests/ref_shim.py) over the oracle emulator core with the synthetic Pokemon-like ROM: per-step reward
    (float64), done, CRC32 of the (72,80,4) observation, SHA-256 of the full emulator state, the wrapper's
-   RAM writes, and the start state.  GPU tests replay the same actions through the CUDA path.
+   RAM writes, the start state, and a fingerprint of every info dict the reference emitted.  Recorded from a booted
+   synthetic game (pokelike_*) and from four of the reference's real Pokemon Red save-states (red_*).  GPU tests replay
+   the same actions through the CUDA path.
 2. ppu_kat.npz -- for a spread of the reference's own PyBoy save-states: the renderer inputs (VRAM, OAM,
    LCD registers, per-scanline parameters) and the framebuffer PyBoy itself rendered from them (2 bits per
    pixel).  These pin the scanline renderer to real PyBoy output.
 """
 import hashlib
+import json
 import sys
 import zlib
 from pathlib import Path
@@ -21,6 +24,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 import __graft_entry__ as g  # noqa: E402
+from helpers import info_fingerprint  # noqa: E402
 from pokegym_b200 import _capi  # noqa: E402
 from pokegym_b200.state_file import parse_state  # noqa: E402
 from pokegym_b200.tools import synth_rom  # noqa: E402
@@ -41,12 +45,15 @@ def wrapper_golden(name, rom_name, start_blob, n_steps, seed, max_episode_steps,
     obs_crc = np.array([zlib.crc32(o.tobytes()) for o in ref["obs"]], dtype=np.uint32)
     state_sha = np.array([np.frombuffer(hashlib.sha256(s).digest(), dtype=np.uint8) for s in ref["states"]])
     writes = np.array([len(w) for w in ref["writes"]], dtype=np.int32)
+    info_steps = [i for i, x in enumerate(ref["infos"]) if x]
+    info_json = [json.dumps(info_fingerprint(ref["infos"][i])) for i in info_steps]
     np.savez_compressed(
         OUT / f"ref_wrapper_{name}.npz", rom_name=rom_name, start_state=np.frombuffer(start_blob, dtype=np.uint8), actions=actions,
         rewards=np.array(ref["rewards"], dtype=np.float64), dones=np.array(ref["dones"], dtype=np.uint8), obs_crc=obs_crc, state_sha=state_sha,
         n_ram_writes=writes, max_episode_steps=max_episode_steps, reset_at=np.array(reset_at, dtype=np.int32),
-        reset_obs_crc=np.array([zlib.crc32(o.tobytes()) for o in ref["reset_obs"]], dtype=np.uint32), last_obs=ref["obs"][-1])
-    print(name, "steps", n_steps, "sum|reward|", float(np.abs(ref["rewards"]).sum()), "nonzero rewards", int(np.count_nonzero(ref["rewards"])))
+        reset_obs_crc=np.array([zlib.crc32(o.tobytes()) for o in ref["reset_obs"]], dtype=np.uint32), last_obs=ref["obs"][-1],
+        info_steps=np.array(info_steps, dtype=np.int32), info_json=np.array(info_json))
+    print(name, "steps", n_steps, "info dicts", len(info_steps), "sum|reward|", float(np.abs(ref["rewards"]).sum()), "nonzero rewards", int(np.count_nonzero(ref["rewards"])))
 
 
 def ppu_golden(n_pick=16):
@@ -76,6 +83,15 @@ def main():
     start = h.save_state(0)
     wrapper_golden("pokelike_a", "pokelike", start, 400, 11, 150, (150, 300), lib)
     wrapper_golden("pokelike_b", "pokelike", start, 250, 12, 20480, (), lib)
+    # real Pokemon Red RAM (party, events, bag, battle / menu state) from the reference's own save-states, driven by the
+    # state-compatible synthetic ROM: pins reward shaping, RAM side effects and the info dict on game data
+    for name, rel in (("red_overworld", "current_state/Bulbasaur.state"), ("red_battle", "bin/checkpoints_battles/bulbasaur/pokemon_ai_14"),
+                      ("red_bill", "bin/checkpoints_bill/pokemon_ai_1005"), ("red_pallet", "bin/checkpoints_pallet/pokemon_ai_105")):
+        p = REF / rel
+        if not p.exists():
+            cands = sorted(p.parent.glob("*"))
+            p = cands[len(cands) // 2]
+        wrapper_golden(name, "pokelike", p.read_bytes(), 60, 7, 40, (45,), lib)
     ppu_golden()
 
 

@@ -1,15 +1,32 @@
 """Shared helpers for the parity tests."""
 import hashlib
+import json
 import zlib
 from pathlib import Path
 
 import numpy as np
 
 from pokegym_b200 import _capi
+from pokegym_b200.info import build_info
 from pokegym_b200.state_file import field_offsets, parse_state, serialize_state
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 SHADE_WORDS = np.array([0xFFFFFF01, 0x99999900, 0x55555500, 0x00000000], dtype="<u4")
+
+
+def info_fingerprint(info):
+    """The reference's info dict (or build_info's) reduced to plain JSON-able data: numbers as floats, the exploration
+    map as (sum, CRC32 of its int64 image), the reference's stray `set` under stats["maps_explored"] as its length."""
+    if isinstance(info, dict):
+        return {str(k): info_fingerprint(v) for k, v in info.items()}
+    if isinstance(info, (set, frozenset)):
+        return float(len(info))
+    if isinstance(info, np.ndarray) and info.ndim:
+        a = np.ascontiguousarray(info.astype(np.int64))
+        return {"sum": float(a.sum()), "crc32": int(zlib.crc32(a.tobytes()))}
+    if isinstance(info, (list, tuple)):
+        return [info_fingerprint(v) for v in info]
+    return float(info)
 
 
 def replay_wrapper_golden(handle, gold, xp=None, to_dev=lambda a: a, to_host=lambda a: a):
@@ -25,6 +42,8 @@ def replay_wrapper_golden(handle, gold, xp=None, to_dev=lambda a: a, to_host=lam
     reset_at = set(int(x) for x in gold["reset_at"])
     handle.reset(obs, max_episode_steps=mes)
     assert zlib.crc32(to_host(obs).tobytes()) == int(gold["reset_obs_crc"][0]), "reset observation differs from the reference"
+    infos = {int(i): json.loads(str(t)) for i, t in zip(gold["info_steps"], gold["info_json"])} if "info_steps" in gold else {}
+    info_row = to_dev(np.zeros((n, _capi.INFO_SCALARS), dtype=np.float64))
     k = 1
     for i, a in enumerate(gold["actions"]):
         if i in reset_at:
@@ -36,6 +55,11 @@ def replay_wrapper_golden(handle, gold, xp=None, to_dev=lambda a: a, to_host=lam
         assert r == float(gold["rewards"][i]), f"step {i}: reward {r!r} != reference {float(gold['rewards'][i])!r}"
         assert d == int(gold["dones"][i]), f"step {i}: done differs"
         assert zlib.crc32(o.tobytes()) == int(gold["obs_crc"][i]), f"step {i}: observation differs from the reference"
+        if i in infos:  # the dict the reference emitted at this step (done / every 10,000 steps), environment.py:1620-1810
+            handle.get_info(info_row)
+            wram = handle.read_mem(0, 0xD700, 0x200)
+            mine = build_info(to_host(info_row)[0], lambda a: int(wram[a - 0xD700]), counts_map=handle.counts_map(0))
+            assert info_fingerprint(mine) == infos[i], f"step {i}: info dict differs from the reference's"
         if i % 25 == 0 or i == len(gold["actions"]) - 1:
             sha = np.frombuffer(hashlib.sha256(handle.save_state(0)).digest(), dtype=np.uint8)
             assert np.array_equal(sha, gold["state_sha"][i]), f"step {i}: emulator state differs (RAM side effects / emulation)"

@@ -6,7 +6,7 @@ from helpers import GOLDEN, check_ppu_kat, replay_wrapper_golden
 from pokegym_b200 import _capi
 
 
-@pytest.mark.parametrize("name", ["pokelike_a", "pokelike_b"])
+@pytest.mark.parametrize("name", ["pokelike_a", "pokelike_b", "red_overworld", "red_battle", "red_bill", "red_pallet"])
 def test_oracle_replays_reference_wrapper_recording(oracle_lib, roms, name):
     gold = np.load(GOLDEN / f"ref_wrapper_{name}.npz")
     h = _capi.Handle(oracle_lib, 1, roms(str(gold["rom_name"])))

@@ -9,7 +9,7 @@ from pokegym_b200 import _capi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["pokelike_a", "pokelike_b"])
+@pytest.mark.parametrize("name", ["pokelike_a", "pokelike_b", "red_overworld", "red_battle", "red_bill", "red_pallet"])
 def test_cuda_replays_reference_wrapper_recording(cuda_lib, roms, name):
     import torch
 

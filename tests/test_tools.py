@@ -91,3 +91,26 @@ def test_halt_edge_rom_cycles_through_every_scenario(oracle_lib, roms):
     assert int(h.read_mem(0, 0xFFA0, 1)[0]) == 5 and joy >= 8 and vblank >= 100 and stat >= 30 and timer >= 12, (vblank, stat, timer, joy)
     assert h.counters().faults == 0
     assert h.save_state(0) != h.save_state(1)
+
+
+def test_pyboy_crosscheck_driver_matches_run_action(oracle_lib, roms):
+    """tools/pyboy_crosscheck.py drives PyBoy the way pyboy_binding.run_action_on_emulator does; on the PyBoy-shaped
+    shim over the oracle core that sequence must leave the same state as one gbenv_run_action call."""
+    import importlib.util
+    from pathlib import Path
+
+    import ref_shim
+    from pokegym_b200 import _capi
+
+    spec = importlib.util.spec_from_file_location("pyboy_crosscheck", Path(__file__).resolve().parents[1] / "tools" / "pyboy_crosscheck.py")
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    rom = roms("pokelike")
+    ref_shim.ShimConfig.rom, ref_shim.ShimConfig.oracle_lib = rom, oracle_lib
+    fake = ref_shim.FakePyBoy("unused.gb")
+    h = _capi.Handle(oracle_lib, 1, rom)
+    for a in (4, 0, 7, 2, 2, 5):
+        tool.pyboy_run_action(fake, ref_shim.WindowEvent, a)
+        h.run_action(np.array([a], np.uint8))
+        assert fake.handle.save_state(0) == h.save_state(0), diff_states(fake.handle.save_state(0), h.save_state(0))
+    assert tool.not_run("x") == 3
