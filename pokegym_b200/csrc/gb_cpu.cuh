@@ -14,9 +14,11 @@ __constant__ uint32_t c_base_desc[512];  // per-opcode base descriptors (pd_buil
 
 __device__ __forceinline__ uint2 pd_decode_bytes(uint32_t ins, uint32_t pc) {  // ins = opcode | op1 << 8 | op2 << 16
     uint32_t op = ins & 0xFF, imm16 = (ins >> 8) & 0xFFFF, imm8 = imm16 & 0xFF;
-    uint32_t x = c_base_desc[op == 0xCB ? (256u | imm8) : op];
-    uint32_t jr = (pc + 2 + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;
-    return make_uint2(x, imm16 | (jr << 16));
+    uint32_t b = c_base_desc[op == 0xCB ? (256u | imm8) : op];
+    uint32_t lo = imm16;
+    if (PD_H(b) == H_JR) lo = (pc + 2 + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;  // branch target
+    if (op == 0xCB) lo = imm8 >> 6;                                        // rotate / BIT / RES / SET
+    return make_uint2(PD_BASE_WORD0(b), lo | (((pc + PD_BASE_LEN(b)) & 0xFFFF) << 16));
 }
 
 // one thread per ROM offset
@@ -112,7 +114,7 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
         const uint32_t dx = d.x, y = PD_Y(dx), z = PD_Z(dx), p = y >> 1;
         const uint32_t imm16 = d.y & 0xFFFF, imm8 = d.y & 0xFF;
         const uint32_t hl = reg_hl(m);
-        uint32_t next_pc = (pc + PD_LEN(dx)) & 0xFFFF;
+        uint32_t next_pc = d.y >> 16;
         cycles = PD_CYC(dx);
         switch (PD_H(dx)) {
         case H_NOP: break;
@@ -164,20 +166,20 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
             break;
         }
         case H_JR:
-            if (y == 0 || condition(m, y & 3)) { next_pc = d.y >> 16; cycles = PD_CYC2(dx); }
+            if (y == 0 || condition(m, y & 3)) { next_pc = imm16; cycles += PD_TAKEN_EXTRA(dx); }
             break;
         case H_JP:
-            if (y == 0 || condition(m, y & 3)) { next_pc = imm16; cycles = PD_CYC2(dx); }
+            if (y == 0 || condition(m, y & 3)) { next_pc = imm16; cycles += PD_TAKEN_EXTRA(dx); }
             break;
         case H_CALL:
-            if (y == 0 || condition(m, y & 3)) { PUSH16(next_pc); next_pc = imm16; cycles = PD_CYC2(dx); }
+            if (y == 0 || condition(m, y & 3)) { PUSH16(next_pc); next_pc = imm16; cycles += PD_TAKEN_EXTRA(dx); }
             break;
         case H_RETI: m.ime = 1;  // fall through
         case H_RET:
             if (y == 0 || condition(m, y & 3)) {
                 next_pc = rd8(m, m.sp) | (rd8(m, (m.sp + 1) & 0xFFFF) << 8);
                 m.sp = (m.sp + 2) & 0xFFFF;
-                cycles = PD_CYC2(dx);
+                cycles += PD_TAKEN_EXTRA(dx);
             }
             break;
         case H_RST: PUSH16(next_pc); next_pc = y * 8; break;
@@ -192,7 +194,7 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
         case H_CB_R:
         case H_CB_HL: {
             const bool mem = PD_H(dx) == H_CB_HL;
-            const uint32_t x = PD_OP(dx) >> 6, f = reg_f(m);
+            const uint32_t x = imm16, f = reg_f(m);  // CB page: word 1 carries opcode bits 6-7
             uint32_t v = mem ? rd8(m, hl) : reg8(m, z), res;
             if (x == 1) {  // BIT: Z from the tested bit, H set, C kept
                 set_f(m, (f & FLAG_C) | FLAG_H | (((v >> y) & 1) ? 0 : FLAG_Z));
@@ -226,10 +228,10 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
             break;
         }
         default: {  // H_RARE
-            const uint32_t op = PD_OP(dx), a = reg_a(m), f = reg_f(m);
+            const uint32_t op = y, a = reg_a(m), f = reg_f(m);  // H_RARE: Y is the whole opcode
             switch (op) {
             case 0x76: m.halted = 1; next_pc = pc; break;              // HALT: PC stays on the HALT byte
-            case 0x10: next_pc = (pc + 2) & 0xFFFF; break;             // STOP skips a byte
+            case 0x10: break;                                          // STOP skips a byte (length 2 in the descriptor)
             case 0xF3: m.ime = 0; break;
             case 0xFB: m.ime = 1; break;  // PyBoy: EI takes effect immediately
             case 0x27: {                                                              // DAA
@@ -250,21 +252,18 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
             case 0x3F: set_f(m, (f & FLAG_Z) | ((f & FLAG_C) ^ FLAG_C)); break;       // CCF
             case 0x08:  // LD (nn),SP: low byte first
                 w0a = imm16; w0v = m.sp & 0xFF; w1a = (imm16 + 1) & 0xFFFF; w1v = m.sp >> 8; wn = 2;
-                next_pc = (pc + 3) & 0xFFFF;
-                cycles = 20;
                 break;
             case 0xE8:
             case 0xF8: {  // ADD SP,e / LD HL,SP+e
                 uint32_t sp = m.sp;
                 set_f(m, (((sp & 0xF) + (imm8 & 0xF)) > 0xF ? FLAG_H : 0) | (((sp & 0xFF) + imm8) > 0xFF ? FLAG_C : 0));
                 uint32_t t = (sp + ((imm8 ^ 0x80) - 0x80)) & 0xFFFF;
-                next_pc = (pc + 2) & 0xFFFF;
-                if (op == 0xE8) { m.sp = t; cycles = 16; }
-                else { set_hl(m, t); cycles = 12; }
+                if (op == 0xE8) m.sp = t;
+                else set_hl(m, t);
                 break;
             }
             case 0xE9: next_pc = hl; break;           // JP HL
-            case 0xF9: m.sp = hl; cycles = 8; break;  // LD SP,HL
+            case 0xF9: m.sp = hl; break;              // LD SP,HL
             default: m.fault = 1; break;  // illegal opcode: PyBoy raises; 1-byte 4-cycle NOP + sticky fault
             }
             break;

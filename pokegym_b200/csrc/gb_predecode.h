@@ -10,15 +10,21 @@
 #pragma once
 #include <stdint.h>
 
-// descriptor word 0
-#define PD_H(x) ((x) & 63u)            // handler
-#define PD_Y(x) (((x) >> 6) & 7u)      // opcode bits 3-5: destination register / ALU op / bit index / condition (see handlers)
-#define PD_Z(x) (((x) >> 9) & 7u)      // opcode bits 0-2: source register
-#define PD_LEN(x) (((x) >> 12) & 3u)
-#define PD_CYC(x) ((((x) >> 14) & 7u) * 4u)   // T-cycles, condition false / unconditional
-#define PD_CYC2(x) ((((x) >> 17) & 7u) * 4u)  // T-cycles, condition true
-#define PD_OP(x) (((x) >> 20) & 0xFFu)        // the opcode byte (CB page: the second byte)
-// descriptor word 1:  imm16 | jr_target << 16
+// descriptor word 0:  handler | taken_extra << 6 | Y << 8 | Z << 16 | cycles << 24   (byte-aligned: one PRMT / shift each)
+//   Y  opcode bits 3-5: destination register / ALU op / bit index / condition (H_RARE: the whole opcode byte)
+//   Z  opcode bits 0-2: source register
+//   cycles  T-cycles, condition false / unconditional;  taken_extra  (T-cycles when the condition holds - cycles) / 4
+// descriptor word 1:  imm16 | next_pc << 16   (H_JR: the branch target instead of imm16; CB page: opcode bits 6-7)
+#define PD_H(x) ((x) & 63u)
+#define PD_TAKEN_EXTRA(x) ((((x) >> 6) & 3u) * 4u)
+#if defined(__CUDA_ARCH__)
+#define PD_Y(x) __byte_perm((x), 0, 0x4441)
+#define PD_Z(x) __byte_perm((x), 0, 0x4442)
+#else
+#define PD_Y(x) (((x) >> 8) & 0xFFu)
+#define PD_Z(x) (((x) >> 16) & 0xFFu)
+#endif
+#define PD_CYC(x) ((x) >> 24)
 
 enum {
     H_SLOW = 0,  // not pre-decodable here (instruction straddles a bank boundary): decode on the fly
@@ -29,9 +35,13 @@ enum {
     H__COUNT
 };
 
+// `len` travels in bits 28-29 of the BASE entry only (pd_split_len strips it); cycles <= 24 needs bits 24-28
 static inline uint32_t pd_make(uint32_t h, uint32_t y, uint32_t z, uint32_t len, uint32_t cyc, uint32_t cyc2, uint32_t op) {
-    return h | (y << 6) | (z << 9) | (len << 12) | ((cyc / 4) << 14) | ((cyc2 / 4) << 17) | (op << 20);
+    if (h == H_RARE) y = op;
+    return h | (((cyc2 - cyc) / 4) << 6) | (y << 8) | (z << 16) | (cyc << 24) | (len << 29);
 }
+#define PD_BASE_LEN(x) ((x) >> 29)
+#define PD_BASE_WORD0(x) ((x) & 0x1FFFFFFFu)
 
 // Per-opcode base descriptors (256 base + 256 CB page).  Cycle counts: the pastraiser table PyBoy 1.6 uses.
 // For conditional control flow the Y field holds the condition: 0 = always, 4..7 = NZ Z NC C.
@@ -49,7 +59,9 @@ static inline void pd_build_base(uint32_t *t) {
                 if (y == 0) d = pd_make(H_NOP, 0, 0, 1, 4, 4, op);
                 else if (y == 3) d = pd_make(H_JR, 0, 0, 2, 12, 12, op);
                 else if (y >= 4) d = pd_make(H_JR, y, 0, 2, 8, 12, op);
-                break;  // LD (nn),SP and STOP: rare
+                else if (y == 1) d = pd_make(H_RARE, y, z, 3, 20, 20, op);  // LD (nn),SP
+                else if (y == 2) d = pd_make(H_RARE, y, z, 2, 4, 4, op);    // STOP skips a byte
+                break;
             case 1: d = q == 0 ? pd_make(H_LD_RP_NN, y, z, 3, 12, 12, op) : pd_make(H_ADD_HL, y, z, 1, 8, 8, op); break;
             case 2: d = q == 0 ? pd_make(H_LD_RP_A, y, z, 1, 8, 8, op) : pd_make(H_LD_A_RP, y, z, 1, 8, 8, op); break;
             case 3: d = pd_make(H_INCDEC_RP, y, z, 1, 8, 8, op); break;
@@ -66,12 +78,15 @@ static inline void pd_build_base(uint32_t *t) {
                 if (y < 4) d = pd_make(H_RET, 4 + y, 0, 1, 8, 20, op);
                 else if (y == 4) d = pd_make(H_LDH_N_A, y, z, 2, 12, 12, op);
                 else if (y == 6) d = pd_make(H_LDH_A_N, y, z, 2, 12, 12, op);
-                break;  // ADD SP,e / LD HL,SP+e: rare
+                else if (y == 5) d = pd_make(H_RARE, y, z, 2, 16, 16, op);  // ADD SP,e
+                else d = pd_make(H_RARE, y, z, 2, 12, 12, op);              // LD HL,SP+e
+                break;
             case 1:
                 if (q == 0) d = pd_make(H_POP, y, z, 1, 12, 12, op);
                 else if (p == 0) d = pd_make(H_RET, 0, 0, 1, 16, 16, op);
                 else if (p == 1) d = pd_make(H_RETI, 0, 0, 1, 16, 16, op);
-                break;  // JP HL, LD SP,HL: rare
+                else if (p == 3) d = pd_make(H_RARE, y, z, 1, 8, 8, op);  // LD SP,HL
+                break;  // JP HL: rare, 4 cycles
             case 2:
                 if (y < 4) d = pd_make(H_JP, 4 + y, 0, 3, 12, 16, op);
                 else if (y == 4) d = pd_make(H_LD_C_A, y, z, 1, 8, 8, op);
