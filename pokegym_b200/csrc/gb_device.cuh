@@ -208,24 +208,21 @@ __device__ __forceinline__ void lcd_set_lcdc(Machine &m, uint32_t v) {
 // 2-bit shade for colour index idx through palette register pal
 __device__ __forceinline__ uint32_t pal_shade(uint32_t pal, uint32_t idx) { return (pal >> (idx * 2)) & 3; }
 
-// spread the low 8 bits of x to the even bit positions of a 16-bit value
-__device__ __forceinline__ uint32_t spread8(uint32_t x) {
-    x = (x | (x << 4)) & 0x0F0Fu;
-    x = (x | (x << 2)) & 0x3333u;
-    x = (x | (x << 1)) & 0x5555u;
-    return x;
+// One tile row (rowdata = plane 0 | plane 1 << 8, leftmost pixel = bit 7 of each plane) -> 8 pixels x 2-bit colour
+// index, leftmost pixel at bit 0.  Both planes are bit-reversed with one BREV, moved to the two half-words with one
+// PRMT and spread to even bit positions together; `xflip` (sprites) skips the reversal.
+__device__ __forceinline__ uint32_t tile_row_indices(uint32_t rowdata, bool xflip = false) {
+    uint32_t x = xflip ? __byte_perm(rowdata, 0, 0x4140) : __byte_perm(__brev(rowdata), 0, 0x4243);  // plane0 | plane1 << 16
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return (x | (x >> 15)) & 0xFFFFu;
 }
 
-// One tile row (two bit-planes, leftmost pixel = bit 7) -> 8 pixels x 2-bit colour index, leftmost at bit 0
-__device__ __forceinline__ uint32_t tile_row_indices(uint32_t b1, uint32_t b2) {
-    uint32_t r1 = __brev(b1) >> 24, r2 = __brev(b2) >> 24;
-    return spread8(r1) | (spread8(r2) << 1);
-}
-
-// map 8 packed 2-bit colour indices through a palette register -> 8 packed 2-bit shades
-__device__ __forceinline__ uint32_t apply_palette16(uint32_t idx16, uint32_t pal) {
-    uint32_t lo = idx16 & 0x5555u, hi = (idx16 >> 1) & 0x5555u;
-    uint32_t m0 = ~lo & ~hi & 0x5555u, m1 = lo & ~hi, m2 = ~lo & hi, m3 = lo & hi;  // one bit per pixel at even positions
+// map packed 2-bit colour indices (8 in a half-word or 16 in a word) through a palette register -> packed 2-bit shades
+__device__ __forceinline__ uint32_t apply_palette(uint32_t idx, uint32_t pal) {
+    uint32_t lo = idx & 0x55555555u, hi = (idx >> 1) & 0x55555555u;
+    uint32_t m0 = ~lo & ~hi & 0x55555555u, m1 = lo & ~hi, m2 = ~lo & hi, m3 = lo & hi;  // one bit per pixel at even positions
     uint32_t s = 0;
     s |= m0 * (pal & 3);
     s |= m1 * ((pal >> 2) & 3);
@@ -261,7 +258,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
                 col++;
                 if (!tds) t = (t ^ 0x80) + 128;
                 uint32_t rowdata = vram_rd16(m, MEM_VRAM + t * 16 + fine_y * 2);
-                uint32_t px = apply_palette16(tile_row_indices(rowdata & 0xFF, rowdata >> 8), bgp);
+                uint32_t px = tile_row_indices(rowdata);  // colour indices; BGP is applied per word below
                 if (nbits < 0) {
                     acc = (uint64_t)(px >> (uint32_t)(-nbits));
                     nbits += 16;
@@ -277,8 +274,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
                 }
             }
         } else {
-            uint32_t fill = pal_shade(bgp, 0) * 0x55555555u;
-            for (uint32_t k = 0; k < ((uint32_t)wstart + 15) >> 4; k++) line[k * ls] = fill;
+            for (uint32_t k = 0; k < ((uint32_t)wstart + 15) >> 4; k++) line[k * ls] = 0;  // colour 0 everywhere
         }
     }
     // ---- window layer, x in [wstart, 160)
@@ -299,7 +295,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
             col++;
             if (!tds) t = (t ^ 0x80) + 128;
             uint32_t rowdata = vram_rd16(m, MEM_VRAM + t * 16 + fine_y * 2);
-            uint32_t px = apply_palette16(tile_row_indices(rowdata & 0xFF, rowdata >> 8), bgp);
+            uint32_t px = tile_row_indices(rowdata);  // colour indices; BGP is applied per word below
             if (first_tile) {
                 px >>= (first & 7) * 2;
                 acc |= (uint64_t)px << lead;
@@ -318,15 +314,28 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
         }
     }
     if (y == 143) m.ly_window = -1;
+    // ---- BG palette: colour indices -> shades, 16 pixels per word
+#pragma unroll
+    for (uint32_t k = 0; k < FB_LINE_WORDS; k++) line[k * ls] = apply_palette(line[k * ls], bgp);
 
     // ---- sprites
     if (lcdc & 0x02) {
         const int height = (lcdc & 0x04) ? 16 : 8;
         int count = 0;
-        for (uint32_t n = 0; n < 40 && count < 10; n++) {
+        // pass 1: which of the 40 OAM entries overlap this line (independent loads, no early exit);
+        // sy <= y < sy + height with sy = Y - 16  <=>  (unsigned)(y + 16 - Y) < height
+        uint32_t hit_lo = 0, hit_hi = 0;
+#pragma unroll
+        for (uint32_t n = 0; n < 32; n++) hit_lo |= (uint32_t)((y + 16 - (mem_rd_word(m, (MEM_HI >> 2) + n) & 0xFF)) < (uint32_t)height) << n;
+#pragma unroll
+        for (uint32_t n = 0; n < 8; n++) hit_hi |= (uint32_t)((y + 16 - (mem_rd_word(m, (MEM_HI >> 2) + 32 + n) & 0xFF)) < (uint32_t)height) << n;
+        // pass 2: the first ten in OAM order, sorted by (x, n)
+        while ((hit_lo | hit_hi) && count < 10) {
+            uint32_t n;
+            if (hit_lo) { n = __ffs(hit_lo) - 1; hit_lo &= hit_lo - 1; }
+            else { n = 32 + __ffs(hit_hi) - 1; hit_hi &= hit_hi - 1; }
             uint32_t e = mem_rd_word(m, (MEM_HI >> 2) + n);  // Y | X<<8 | tile<<16 | attr<<24
-            int sy = (int)(e & 0xFF) - 16;
-            if (sy <= (int)y && (int)y < sy + height) {
+            {
                 int sx = (int)((e >> 8) & 0xFF) - 8;
                 // insertion into ascending (x, n) order; key = (sx + 8) << 8 | n keeps it unsigned
                 uint32_t key = ((uint32_t)(sx + 8) << 8) | n;
@@ -348,14 +357,9 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
             int dy = (int)y - sy;
             uint32_t yy = (attr & 0x40) ? (uint32_t)(height - dy - 1) : (uint32_t)dy;
             uint32_t rowdata = vram_rd16(m, MEM_VRAM + tile * 16 + yy * 2);
-            uint32_t b1 = rowdata & 0xFF, b2 = rowdata >> 8;
-            if (attr & 0x20) {  // x flip: leftmost pixel = bit 0
-                b1 = __brev(b1) >> 24;
-                b2 = __brev(b2) >> 24;
-            }
-            uint32_t idx16 = tile_row_indices(b1, b2);
+            uint32_t idx16 = tile_row_indices(rowdata, attr & 0x20);  // x flip: leftmost pixel = bit 0
             uint32_t opaque = (idx16 | (idx16 >> 1)) & 0x5555u;  // 1 per non-transparent pixel (even bit)
-            uint32_t shades = apply_palette16(idx16, (attr & 0x10) ? M_OBP1(m) : M_OBP0(m));
+            uint32_t shades = apply_palette(idx16, (attr & 0x10) ? M_OBP1(m) : M_OBP0(m));
             // clip to the screen
             if (sx < 0) {
                 uint32_t cut = (uint32_t)(-sx) * 2;
