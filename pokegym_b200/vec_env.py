@@ -156,6 +156,12 @@ class VecEnvironment:
                 self.reset(mask=d)
         return obs.view(self.num_envs, *OBS_SHAPE), self._reward, done, done, {}
 
+    @staticmethod
+    def compact_view(obs):
+        """Optional 1+1-channel view for new policies: the reference's channels 0-2 are the same grey level,
+        so `obs[..., 2:]` = (grey, visited) carries everything.  A strided view of the same memory, no copy."""
+        return obs[..., 2:]
+
     def info(self):
         """Per-env info rows: float64 [N, 64]; column names in pokegym_b200.info.INFO_NAMES."""
         self.handle.get_info(self._info, stream=self._stream())

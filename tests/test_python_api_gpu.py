@@ -57,6 +57,11 @@ def test_vec_environment_rollout_and_auto_reset(cuda_lib, roms):
     assert seen_done
     s = vec.info_sum().cpu().numpy()
     assert s[0] == n
+    c = VecEnvironment.compact_view(obs)  # (grey, visited): channels 0-2 of the reference layout are identical
+    assert c.shape == (n, 72, 80, 2) and c.data_ptr() == obs.data_ptr() + 2
+    assert torch.equal(obs[..., 0], c[..., 0]) and torch.equal(obs[..., 1], c[..., 0]) and torch.equal(obs[..., 3], c[..., 1])
+    full = vec.full_info(5)  # complete reference-shaped info dict for one env of the batch
+    assert full["stats"]["step"] >= 1 and len(full["silph_co_events_aggregate"]) == 53
     ad = PufferVecAdaptor(vec)
     ad.async_reset()
     ad.send(torch.zeros(n, dtype=torch.uint8, device="cuda"))
