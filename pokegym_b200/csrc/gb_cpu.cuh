@@ -62,8 +62,19 @@ __device__ __forceinline__ uint32_t rd8(Machine &m, uint32_t a) {  // Motherboar
                     m.pal | (m.ie << 24), ((m.div + (m.divc >> 8)) & 0xFF) | m.tmr, m.iflag);
 }
 
-__device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict__ rom_dec) {
-    uint32_t wn = 0, w0a = 0, w0v = 0, w1a = 0, w1v = 0;  // deferred bus writes, issued in order w0, w1
+// Bus writes of one instruction, deferred so that a single write site exists (issued in order w0, w1).
+struct DeferredWrites {
+    uint32_t n, a0, v0, a1, v1;
+};
+
+__device__ __forceinline__ void cpu_commit_writes(Machine &m, const DeferredWrites &w) {
+    for (uint32_t i = 0; i < w.n; i++) bus_write_full(m, i ? w.a1 : w.a0, i ? w.v1 : w.v0);
+}
+
+// Executes one CPU.tick; the instruction's bus writes are returned in `dw` and must be committed by the caller
+// (cpu_commit_writes) before anything else observes the machine.
+__device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict__ rom_dec, DeferredWrites &dw) {
+    uint32_t wn = 0, w0a = 0, w0v = 0, w1a = 0, w1v = 0;
     uint32_t cycles = 0;
 #define PUSH16(val)                                  \
     do {                                             \
@@ -98,7 +109,7 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
             m.halted = 0;
             m.pc = (m.pc + 1) & 0xFFFF;
         }
-        if (execute && m.halted) return 4;
+        if (execute && m.halted) { dw.n = 0; return 4; }
     }
     if (execute) {
         const uint32_t pc = m.pc;
@@ -273,8 +284,7 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
         m.n_instr++;
         m.iq = 0;
     }
-    // ---- write phase
-    for (uint32_t i = 0; i < wn; i++) bus_write_full(m, i ? w1a : w0a, i ? w1v : w0v);
+    dw.n = wn; dw.a0 = w0a; dw.v0 = w0v; dw.a1 = w1a; dw.v1 = w1v;
 #undef PUSH16
 #undef WRITE8
     return cycles;

@@ -3,11 +3,11 @@
 #include "gb_cpu.cuh"
 #include "gb_device.cuh"
 
+#ifndef STEP_THREADS
 #define STEP_THREADS 128
-#ifndef STEP_MIN_BLOCKS
+#endif
 #ifndef STEP_MIN_BLOCKS
 #define STEP_MIN_BLOCKS 5
-#endif
 #endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
@@ -82,14 +82,21 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
             } else {
                 bool event;
                 do {
-                    uint32_t cycles = cpu_step(m, p.d.rom_dec);
-                    if (m.halted | (m.tmr & 0x04000000u)) {  // rare: HALT fast-forward and/or a running TIMA
-                        if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
-                            int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
-                            int c = a < b ? a : b;
-                            cycles = c < 0 ? 0 : (uint32_t)c;
+                    DeferredWrites dw;
+                    uint32_t cycles = cpu_step(m, p.d.rom_dec, dw);
+                    // one divergent region for everything that is not plain register work: stores, HALT, a running TIMA
+                    if (dw.n | m.halted | (m.tmr & 0x04000000u)) {
+                        cpu_commit_writes(m, dw);
+                        if (m.halted | (m.tmr & 0x04000000u)) {
+                            if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
+                                int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
+                                int c = a < b ? a : b;
+                                cycles = c < 0 ? 0 : (uint32_t)c;
+                            }
+                            timer_tick(m, cycles);
+                        } else {
+                            m.divc += cycles;
                         }
-                        timer_tick(m, cycles);
                     } else {
                         m.divc += cycles;  // Timer.tick with the timer stopped: only DIV advances (kept lazily)
                     }
