@@ -86,42 +86,48 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
     } while (0)
 #define WRITE8(addr, val) do { w0a = (addr) & 0xFFFF; w0v = (val); wn = 1; } while (0)
 
-    bool execute = true;
-    // One cheap predicate guards everything that is not plain execution (pending interrupt, HALT, PyBoy's
-    // interrupt_queued latch): on the hot path this is two logic ops and a never-taken branch.
-    if (m.halted | m.iq | (m.iflag & m.ie & 0x1F)) {
-        if (!m.iq) {
-            uint32_t pending = m.iflag & m.ie & 0x1F;
-            if (pending) {  // CPU.handle_interrupt for the highest-priority pending source
-                uint32_t bit = pending & (0u - pending);
-                if (m.halted) m.pc = (m.pc + 1) & 0xFFFF;
-                if (m.ime) {
-                    m.iflag ^= bit;
-                    PUSH16(m.pc);
-                    m.pc = 0x40 + 8 * (31 - __clz(bit));
-                    m.ime = 0;
+    bool execute = true, decoded = false;
+    uint32_t pc = m.pc;
+    uint2 d = make_uint2(0, 0);
+    // One divergent region guards everything that is not plain execution of a pre-decoded instruction: pending
+    // interrupt, HALT, PyBoy's interrupt_queued latch, RAM-resident code and instructions whose operands straddle a
+    // 16 KiB bank boundary (the last three bytes of a bank; k_predecode_rom marks them H_SLOW).  All inputs of the
+    // predicate are in registers, so the hot path pays two logic ops, a compare and one never-taken branch.
+    const uint32_t attention = m.halted | m.iq | (m.iflag & m.ie & 0x1F);
+    if (attention | (uint32_t)(pc >= 0x8000) | (uint32_t)((pc & 0x3FFF) >= 0x3FFD)) {
+        if (attention) {
+            if (!m.iq) {
+                uint32_t pending = m.iflag & m.ie & 0x1F;
+                if (pending) {  // CPU.handle_interrupt for the highest-priority pending source
+                    uint32_t bit = pending & (0u - pending);
+                    if (m.halted) m.pc = (m.pc + 1) & 0xFFFF;
+                    if (m.ime) {
+                        m.iflag ^= bit;
+                        PUSH16(m.pc);
+                        m.pc = 0x40 + 8 * (31 - __clz(bit));
+                        m.ime = 0;
+                    }
+                    m.iq = 1;
+                    m.halted = 0;
+                    execute = false;
                 }
-                m.iq = 1;
+            } else if (m.halted) {  // debugger-only path in PyBoy: halted with a queued interrupt
                 m.halted = 0;
-                execute = false;
+                m.pc = (m.pc + 1) & 0xFFFF;
             }
-        } else if (m.halted) {  // debugger-only path in PyBoy: halted with a queued interrupt
-            m.halted = 0;
-            m.pc = (m.pc + 1) & 0xFFFF;
+            if (execute && m.halted) { dw.n = 0; return 4; }
+            pc = m.pc;
         }
-        if (execute && m.halted) { dw.n = 0; return 4; }
-    }
-    if (execute) {
-        const uint32_t pc = m.pc;
-        // ---- fetch: one unconditional descriptor load (RAM code reads entry 0 and discards it); byte-wise decode
-        // only for RAM code and bank-straddling instructions
-        const bool in_rom = pc < 0x8000;
-        uint2 d = __ldg(rom_dec + (in_rom ? (pc < 0x4000 ? pc : pc + m.rom_off) : 0u));
-        if (!in_rom || PD_H(d.x) == H_SLOW) {
+        if (execute && (pc >= 0x8000 || (pc & 0x3FFF) >= 0x3FFD)) {  // byte-wise decode through the bus
             uint32_t ins = 0;
             for (uint32_t i = 0; i < 3; i++) ins |= rd8(m, (pc + i) & 0xFFFF) << (8 * i);
             d = pd_decode_bytes(ins, pc);
+            decoded = true;
         }
+    }
+    if (execute) {
+        // ---- fetch: one descriptor load replaces opcode fetch, operand fetch and decode
+        if (!decoded) d = __ldg(rom_dec + (pc < 0x4000 ? pc : pc + m.rom_off));
         const uint32_t dx = d.x, y = PD_Y(dx), z = PD_Z(dx), p = y >> 1;
         const uint32_t imm16 = d.y & 0xFFFF, imm8 = d.y & 0xFF;
         const uint32_t hl = reg_hl(m);
