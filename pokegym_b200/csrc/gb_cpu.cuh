@@ -62,29 +62,32 @@ __device__ __forceinline__ uint32_t rd8(Machine &m, uint32_t a) {  // Motherboar
                     m.pal | (m.ie << 24), ((m.div + (m.divc >> 8)) & 0xFF) | m.tmr, m.iflag);
 }
 
-// Bus writes of one instruction, deferred so that a single write site exists (issued in order w0, w1).
+// Bus writes of one instruction, deferred so that a single write site exists.  n = 0 none; 1: one byte (v & 0xFF) at a;
+// 2: low byte of v at a, then high byte at a - 1 (pushes); 3: low byte at a, then high byte at a + 1 (LD (nn),SP).
 struct DeferredWrites {
-    uint32_t n, a0, v0, a1, v1;
+    uint32_t n, a, v;
 };
 
 __device__ __forceinline__ void cpu_commit_writes(Machine &m, const DeferredWrites &w) {
-    for (uint32_t i = 0; i < w.n; i++) bus_write_full(m, i ? w.a1 : w.a0, i ? w.v1 : w.v0);
+    const uint32_t count = w.n > 1 ? 2u : w.n, second = (w.n == 2 ? w.a - 1 : w.a + 1) & 0xFFFF;
+    for (uint32_t i = 0; i < count; i++) bus_write_full(m, i ? second : w.a, i ? (w.v >> 8) & 0xFF : w.v & 0xFF);
 }
 
 // Executes one CPU.tick; the instruction's bus writes are returned in `dw` and must be committed by the caller
 // (cpu_commit_writes) before anything else observes the machine.
 __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict__ rom_dec, DeferredWrites &dw) {
-    uint32_t wn = 0, w0a = 0, w0v = 0, w1a = 0, w1v = 0;
+    // only `wn` is initialised: address / value are read solely when wn != 0
+    uint32_t wn = 0, wa, wv;
     uint32_t cycles = 0;
-#define PUSH16(val)                                  \
-    do {                                             \
-        uint32_t _v = (val);                         \
-        w0a = (m.sp - 1) & 0xFFFF; w0v = _v >> 8;    \
-        w1a = (m.sp - 2) & 0xFFFF; w1v = _v & 0xFF;  \
-        wn = 2;                                      \
-        m.sp = (m.sp - 2) & 0xFFFF;                  \
+#define PUSH16(val)                                                          \
+    do {  /* high byte at SP-1 first, then low byte at SP-2 */               \
+        uint32_t _v = (val);                                                 \
+        wa = (m.sp - 1) & 0xFFFF;                                            \
+        wv = __byte_perm(_v, 0, 0x4401); /* (_v >> 8 & 0xFF) | (_v & 0xFF) << 8 */ \
+        wn = 2;                                                              \
+        m.sp = (m.sp - 2) & 0xFFFF;                                          \
     } while (0)
-#define WRITE8(addr, val) do { w0a = (addr) & 0xFFFF; w0v = (val); wn = 1; } while (0)
+#define WRITE8(addr, val) do { wa = (addr) & 0xFFFF; wv = (val); wn = 1; } while (0)
 
     bool execute = true, decoded = false;
     uint32_t pc = m.pc;
@@ -268,7 +271,7 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
             case 0x37: set_f(m, (f & FLAG_Z) | FLAG_C); break;                        // SCF
             case 0x3F: set_f(m, (f & FLAG_Z) | ((f & FLAG_C) ^ FLAG_C)); break;       // CCF
             case 0x08:  // LD (nn),SP: low byte first
-                w0a = imm16; w0v = m.sp & 0xFF; w1a = (imm16 + 1) & 0xFFFF; w1v = m.sp >> 8; wn = 2;
+                wa = imm16; wv = m.sp; wn = 3;
                 break;
             case 0xE8:
             case 0xF8: {  // ADD SP,e / LD HL,SP+e
@@ -290,7 +293,7 @@ __device__ __forceinline__ uint32_t cpu_step(Machine &m, const uint2 *__restrict
         m.n_instr++;
         m.iq = 0;
     }
-    dw.n = wn; dw.a0 = w0a; dw.v0 = w0v; dw.a1 = w1a; dw.v1 = w1v;
+    dw.n = wn; dw.a = wa; dw.v = wv;
 #undef PUSH16
 #undef WRITE8
     return cycles;
