@@ -667,25 +667,20 @@ __device__ __forceinline__ bool condition(const Machine &m, uint32_t cc) {  // N
     return (bit != 0) == ((cc & 1) != 0);
 }
 
-// 8-bit ALU group (ADD ADC SUB SBC AND XOR OR CP) on A with operand v
+// 8-bit ALU group (ADD ADC SUB SBC AND XOR OR CP) on A with operand v.  Branch-free: in this kernel a divergent
+// region costs about as much as twenty ALU instructions, and lanes running different ALU ops stay converged.
+// Subtraction is addition of the complement with inverted carry-in; its H and C flags are the inverted carries.
 __device__ __forceinline__ void alu8(Machine &m, uint32_t op, uint32_t v) {
-    uint32_t a = reg_a(m), f = reg_f(m), carry = (f >> 4) & 1, res, nf;
-    if (op < 4 || op == 7) {
-        bool sub = (op & 2) || op == 7;
-        uint32_t cin = (op & 1) && op != 7 ? carry : 0;
-        if (!sub) {
-            res = a + v + cin;
-            nf = (((a & 0xF) + (v & 0xF) + cin) > 0xF ? FLAG_H : 0) | (res > 0xFF ? FLAG_C : 0);
-        } else {
-            res = a - v - cin;
-            nf = FLAG_N | (((a & 0xF) < (v & 0xF) + cin) ? FLAG_H : 0) | ((a < v + cin) ? FLAG_C : 0);
-        }
-        res &= 0xFF;
-        if (res == 0) nf |= FLAG_Z;
-        if (op == 7) res = a;
-    } else {
-        res = op == 4 ? (a & v) : op == 5 ? (a ^ v) : (a | v);
-        nf = (op == 4 ? FLAG_H : 0) | (res == 0 ? FLAG_Z : 0);
-    }
-    set_af(m, res, nf);
+    const uint32_t a = reg_a(m), carry = (reg_f(m) >> 4) & 1;
+    const bool logic = (op - 4u) < 3u;             // AND XOR OR
+    const bool sub = (op == 2) | (op == 3) | (op == 7);  // SUB SBC CP
+    const uint32_t cin = (op & 1) & (op < 4) ? carry : 0;   // ADC / SBC only
+    const uint32_t x = sub ? (v ^ 0xFF) : v, c0 = sub ? (cin ^ 1) : cin;
+    const uint32_t sum = a + x + c0;
+    const uint32_t hc = (((a & 0xF) + (x & 0xF) + c0) >> 4) & 1, cc = (sum >> 8) & 1;  // carries out of bit 3 / bit 7
+    const uint32_t lres = op == 4 ? (a & v) : op == 5 ? (a ^ v) : (a | v);
+    const uint32_t res = logic ? lres : (sum & 0xFF);
+    uint32_t nf = logic ? (op == 4 ? FLAG_H : 0) : (((hc ^ (uint32_t)sub) ? FLAG_H : 0) | ((cc ^ (uint32_t)sub) ? FLAG_C : 0) | (sub ? FLAG_N : 0));
+    if (res == 0) nf |= FLAG_Z;
+    set_af(m, op == 7 ? a : res, nf);
 }
