@@ -118,10 +118,10 @@ int gbenv_reset_host(gbenv_t *h, const uint8_t *mask_host, int max_episode_steps
 int gbenv_get_info(gbenv_t *h, double *info_dev, void *stream);
 /* Sum of the info rows over envs (+ env count in slot 0): the vector ranks all-reduce over NCCL. */
 int gbenv_reduce_info(gbenv_t *h, double *sum_dev /* GBENV_INFO_SCALARS */, void *stream);
-/* `pokemon_exploration_map` (environment.py:448,648-679,1624): int32[444*436] of one env.  The maps
- * (774 KB per env) are allocated when they fit in 4 GiB (about 5,500 envs per GPU) or when GBENV_COUNTS_MAP=1;
- * otherwise this returns GBENV_E_ARG and the info slot GBI_COORD_SUM (np.sum of the map) stays 0 -- the map is
- * logging output and never feeds the reward or the observation.                                  */
+/* `pokemon_exploration_map` (environment.py:448,648-679,1624): int32[444*436] of one env.  Stored dense
+ * (774 KB per env) while all maps fit in 4 GiB, otherwise as a per-env hash of the cells the env has touched
+ * (2 GiB budget; env GBENV_COUNTS_MAP=dense|sparse|0, GBENV_COUNTS_SLOTS=<power of two>), from which this call
+ * rebuilds the dense image.  A full hash stops tracking new cells and is reported through counters.faults.   */
 int gbenv_counts_map(gbenv_t *h, int env, int32_t *map_host);
 
 /* ---- diagnostics ----------------------------------------------------------------------------*/

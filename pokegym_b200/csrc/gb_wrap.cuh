@@ -32,6 +32,7 @@ struct CutCoord {
 struct WrapState {
     // env-lifetime
     int32_t reset_count, is_dead, last_map, initial_template;
+    int32_t cm_used, cm_pad;  // entries in this env's sparse heat map
     double item_reward[5];
     long long coord_sum;  // running np.sum(counts_map)
     // per-episode
@@ -52,7 +53,9 @@ struct WrapState {
 struct WrapArrays {
     WrapState *state;     // [n_envs]
     uint32_t *visited;    // [n_envs][slots][VIS_MAP_WORDS]
-    int32_t *counts_map;  // [n_envs][444*436] or null
+    int32_t *counts_map;  // dense heat maps [n_envs][444*436], or null when they do not fit (then cm_hash is used)
+    uint2 *cm_hash;       // sparse heat maps [n_envs][cm_cap]: {cell index + 1 (0 = empty), count}, linear probing
+    int cm_cap;           // power of two
     int slots;
 };
 
@@ -226,11 +229,32 @@ __device__ inline double wrap_after_emulation(const WrapArrays &w, WrapState &s,
     update_last_map_id(m, s);  // :1352
     double exploration_reward = (s.used_cut < 1 ? 0.02 : 0.1) * (double)s.n_seen_coords;  // :1375
     int glob_r = r + c_map_offsets[map_n].y, glob_c = c + c_map_offsets[map_n].x;          // game_map.py:11-18
-    if (w.counts_map && glob_r < COUNTS_H && glob_c < COUNTS_W) {  // update_heat_map :648-679
-        int32_t *cell = w.counts_map + (size_t)env * COUNTS_H * COUNTS_W + glob_r * COUNTS_W + glob_c;
-        int32_t old = *cell, neu = (s.last_map == map_n || s.last_map == -1) ? old + 1 : -1;
-        *cell = neu;
-        s.coord_sum += (long long)neu - old;
+    if (glob_r < COUNTS_H && glob_c < COUNTS_W) {  // update_heat_map :648-679
+        const bool same_map = s.last_map == map_n || s.last_map == -1;
+        const uint32_t cell_id = (uint32_t)(glob_r * COUNTS_W + glob_c);
+        if (w.counts_map) {
+            int32_t *cell = w.counts_map + (size_t)env * COUNTS_H * COUNTS_W + cell_id;
+            int32_t old = *cell, neu = same_map ? old + 1 : -1;
+            *cell = neu;
+            s.coord_sum += (long long)neu - old;
+        } else if (w.cm_hash) {  // big batches: only the cells this env has touched are stored
+            uint2 *tab = w.cm_hash + (size_t)env * w.cm_cap;
+            const uint32_t key = cell_id + 1, mask = (uint32_t)w.cm_cap - 1;
+            uint32_t i = (key * 2654435761u) >> 7 & mask;
+            int probes = 0;
+            for (; probes < w.cm_cap; probes++, i = (i + 1) & mask) {
+                uint2 e = tab[i];
+                if (e.x == key || e.x == 0) {
+                    if (e.x == 0 && s.cm_used >= w.cm_cap - (w.cm_cap >> 3)) { probes = w.cm_cap; break; }  // keep 1/8 free
+                    int32_t old = e.x ? (int32_t)e.y : 0, neu = same_map ? old + 1 : -1;
+                    if (e.x == 0) s.cm_used++;
+                    tab[i] = make_uint2(key, (uint32_t)neu);
+                    s.coord_sum += (long long)neu - old;
+                    break;
+                }
+            }
+            if (probes >= w.cm_cap) s.overflow = 1;  // table full: the cell is not tracked (reported through `faults`)
+        }
     }
     s.last_map = map_n;
     if (map_n != s.prev_map_n) {  // :1378-1382

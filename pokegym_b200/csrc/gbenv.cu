@@ -259,7 +259,7 @@ extern "C" int gbenv_destroy(gbenv *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &t : h->templates) cudaFree(t.d_image);
     cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree((void *)h->d.rom); cudaFree((void *)h->d.rom_dec);
-    cudaFree(h->w.state); cudaFree(h->w.visited); cudaFree(h->w.counts_map);
+    cudaFree(h->w.state); cudaFree(h->w.visited); cudaFree(h->w.counts_map); cudaFree(h->w.cm_hash);
     cudaFree(h->d_counters); cudaFree(h->d_stage_image); cudaFree(h->d_stage_buf); cudaFree(h->d_info_rows);
     cudaFree(h->d_env_ids); cudaFree(h->d_mask); cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_reward);
     for (auto &slot : h->ev)
@@ -336,9 +336,25 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     }
     ALLOC(h->w.state, sizeof(WrapState) * (size_t)n_envs);
     ALLOC(h->w.visited, (size_t)n_envs * slots * per_slot);
-    bool want_counts = (size_t)n_envs * COUNTS_H * COUNTS_W * 4 <= ((size_t)4 << 30);
-    if (const char *ev = getenv("GBENV_COUNTS_MAP")) want_counts = atoi(ev) != 0;
-    if (want_counts) ALLOC(h->w.counts_map, (size_t)n_envs * COUNTS_H * COUNTS_W * sizeof(int32_t));
+    {   // heat maps (environment.py:648-679): dense 444x436 int32 per env while they fit in 4 GiB, else a per-env hash of the
+        // cells actually touched (one new cell per step at most), sized to a 2 GiB budget; GBENV_COUNTS_MAP=dense|sparse|0
+        bool dense = (size_t)n_envs * COUNTS_H * COUNTS_W * 4 <= ((size_t)4 << 30), sparse = !dense;
+        if (const char *ev = getenv("GBENV_COUNTS_MAP")) {
+            dense = !strcmp(ev, "dense") || !strcmp(ev, "1");
+            sparse = !strcmp(ev, "sparse");
+        }
+        if (dense) ALLOC(h->w.counts_map, (size_t)n_envs * COUNTS_H * COUNTS_W * sizeof(int32_t));
+        if (sparse) {
+            int cap = 65536;
+            while (cap > 1024 && (size_t)n_envs * cap * sizeof(uint2) > ((size_t)2 << 30)) cap >>= 1;
+            if (const char *ev = getenv("GBENV_COUNTS_SLOTS")) {
+                int v = atoi(ev);
+                if (v >= 16 && v <= (1 << 18) && (v & (v - 1)) == 0) cap = v;
+            }
+            h->w.cm_cap = cap;
+            ALLOC(h->w.cm_hash, (size_t)n_envs * cap * sizeof(uint2));
+        }
+    }
     ALLOC(h->d_counters, 8 * sizeof(unsigned long long));
     ALLOC(h->d_stage_image, IMG_WORDS * sizeof(uint32_t));
     ALLOC(h->d_stage_buf, 0x10000);
@@ -652,9 +668,17 @@ extern "C" int gbenv_reduce_info(gbenv *h, double *sum_dev, void *stream) {
 
 extern "C" int gbenv_counts_map(gbenv *h, int env, int32_t *map_host) {
     if (!h || env < 0 || env >= h->n || !map_host) return fail(h, GBENV_E_ARG, "gbenv_counts_map: bad argument");
-    if (!h->w.counts_map) return fail(h, GBENV_E_ARG, "gbenv_counts_map: exploration map tracking is disabled (GBENV_COUNTS_MAP=0 or too many envs)");
+    if (!h->w.counts_map && !h->w.cm_hash) return fail(h, GBENV_E_ARG, "gbenv_counts_map: exploration map tracking is disabled (GBENV_COUNTS_MAP=0)");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    if (!h->w.counts_map) {  // sparse: rebuild the dense image from this env's hash entries
+        std::vector<uint2> tab((size_t)h->w.cm_cap);
+        CK(cudaMemcpy(tab.data(), h->w.cm_hash + (size_t)env * h->w.cm_cap, tab.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+        memset(map_host, 0, (size_t)COUNTS_H * COUNTS_W * 4);
+        for (const uint2 &e : tab)
+            if (e.x) map_host[e.x - 1] = (int32_t)e.y;
+        return GBENV_OK;
+    }
     CK(cudaMemcpy(map_host, h->w.counts_map + (size_t)env * COUNTS_H * COUNTS_W, (size_t)COUNTS_H * COUNTS_W * 4, cudaMemcpyDeviceToHost));
     return GBENV_OK;
 }
