@@ -182,7 +182,7 @@ class VecEnvironment:
         wram = self.handle.read_mem(env, 0xD700, 0x200)  # every event flag lives in 0xD7B1..0xD838
         try:
             cm = self.handle.counts_map(env).astype(np.float64)
-        except _capi.GbEnvError:  # counts maps disabled for very large batches (GBENV_COUNTS_MAP=0)
+        except _capi.GbEnvError:  # heat maps switched off (GBENV_COUNTS_MAP=0)
             cm = None
         return build_info(row, lambda a: int(wram[a - 0xD700]), counts_map=cm, reward_scale=self.reward_scale)
 
