@@ -3,11 +3,13 @@
 #include "gb_cpu.cuh"
 #include "gb_device.cuh"
 
+// 64-thread blocks, 10 per SM (96 registers): the same 20 resident warps per SM as 128 x 5, but a finer grain for the
+// block scheduler, so SMs differ by one block of two warps instead of four (+1 % at 4,096 and 32,768 envs)
 #ifndef STEP_THREADS
-#define STEP_THREADS 128
+#define STEP_THREADS 64
 #endif
 #ifndef STEP_MIN_BLOCKS
-#define STEP_MIN_BLOCKS 5
+#define STEP_MIN_BLOCKS 10
 #endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
