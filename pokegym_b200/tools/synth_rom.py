@@ -1873,5 +1873,6 @@ def rom_catalog() -> Dict[str, Tuple]:
         "pokelike_timer": (build_pokelike_rom, {"timer": True}),
         "busy": (build_pokelike_rom, {"always_busy": True}),
         "conformance": (build_conformance_rom, {}),
+        "conformance_b": (build_conformance_rom, {"seed": 99, "n_blocks": 900}),  # second instruction stream / interrupt phase
         "halt_edge": (build_halt_edge_rom, {}),
     }
