@@ -170,14 +170,15 @@ def test_readme_config_72_envs_long_run(cuda_lib, oracle_lib, roms):
     _assert_same_states(gpu, cpu, range(n), "end of long run")
 
 
-def test_full_size_batch_matches_replicated_small_batch(cuda_lib, oracle_lib, roms):
-    """BASELINE.json's per-GPU target size (32,768 envs) through a size-independent property: env i is given the start
-    state and the actions of env (i mod 64), so every output must equal the 64-env oracle run replicated 512 times.
-    Exercises tile/lane indexing, the envs-per-warp heuristic (16 at this size), the visited-map slot budget and the
-    sparse heat maps."""
+@pytest.mark.parametrize("n,steps", [(32768, 3), (4096, 120)])
+def test_full_size_batch_matches_replicated_small_batch(cuda_lib, oracle_lib, roms, n, steps):
+    """BASELINE.json's batch sizes (32,768 envs: the per-GPU target; 4,096 envs: the benchmark configuration, 2 envs per
+    warp, run for 120 steps across an episode boundary) through a size-independent property: env i is given the start
+    state and the actions of env (i mod 64), so every output must equal the 64-env oracle run replicated.
+    Exercises tile/lane indexing, the envs-per-warp heuristic, the visited-map slot budget and the sparse heat maps."""
     import torch
 
-    n, base, steps = 32768, 64, 3
+    base = 64
     rom = roms("pokelike")
     gpu = _capi.Handle(cuda_lib, n, rom, 0)
     cpu = _capi.Handle(oracle_lib, base, rom)
@@ -189,8 +190,8 @@ def test_full_size_batch_matches_replicated_small_batch(cuda_lib, oracle_lib, ro
     oc = np.zeros((base, _capi.OBS_BYTES), dtype=np.uint8)
     rc = np.zeros(base)
     dc = np.zeros(base, dtype=np.uint8)
-    gpu.reset(og, max_episode_steps=2)
-    cpu.reset(oc, max_episode_steps=2)
+    gpu.reset(og, max_episode_steps=50)
+    cpu.reset(oc, max_episode_steps=50)
     rng = np.random.default_rng(77)
     reps = n // base
     for s in range(steps):
@@ -202,7 +203,10 @@ def test_full_size_batch_matches_replicated_small_batch(cuda_lib, oracle_lib, ro
         o = og.view(reps, base, _capi.OBS_BYTES)
         ref = torch.from_numpy(oc).cuda()
         assert bool((o == ref[None]).all()), f"obs differs at step {s}"
-    for e in (0, 63, 64, 12345, 20000, n - 1):
+        if dc.all() and s % 50 == 49:  # episode end: reset everything, as a vectoriser would
+            gpu.reset(og, max_episode_steps=50)
+            cpu.reset(oc, max_episode_steps=50)
+    for e in (0, 63, 64, n // 3, n // 2 + 5, n - 1):
         assert gpu.save_state(e) == cpu.save_state(e % base), e
     info = torch.zeros(_capi.INFO_SCALARS, dtype=torch.float64, device="cuda")
     gpu.reduce_info(info)
@@ -210,8 +214,8 @@ def test_full_size_batch_matches_replicated_small_batch(cuda_lib, oracle_lib, ro
     cpu.reduce_info(ic)
     ig = info.cpu().numpy()
     assert np.allclose(ig, ic * reps, rtol=1e-12, atol=0), np.nonzero(ig != ic * reps)
-    # at this size the heat maps are kept as per-env hashes of the touched cells; the dense image is rebuilt on request
-    for e in (1, 4097, n - 2):
+    # 32,768 envs keep their heat maps as per-env hashes of the touched cells (dense image rebuilt on request), 4,096 dense
+    for e in (1, n // 2 + 1, n - 2):
         assert np.array_equal(gpu.counts_map(e), cpu.counts_map(e % base)), e
     assert gpu.counters().faults == 0
 
