@@ -37,6 +37,16 @@ ROLLOUT_T = 32
 WORKLOAD = "pokelike synthetic ROM (MBC3, ~25% busy frames), random actions, full reward shaping, obs into device rollout u8[32,E,72,80,4]"
 
 
+def workload_name(args) -> str:
+    from pokegym_b200.tools import synth_rom
+
+    if args.rom == "pokelike" and not args.state:
+        return WORKLOAD
+    what = f"synthetic ROM '{args.rom}'" if args.rom in synth_rom.rom_catalog() else f"user ROM {Path(args.rom).name}"
+    start = f"reset from {Path(args.state).name}" if args.state else "booted for 60 frames"
+    return f"{what}, {start}, random actions, full reward shaping, obs into device rollout u8[32,E,72,80,4]"
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -44,7 +54,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rom", default="pokelike")
+    ap.add_argument("--rom", default=os.environ.get("POKEGYM_ROM", "pokelike"), help="synthetic ROM name or path to a .gb file")
+    ap.add_argument("--state", default=None, help="PyBoy .state file every env resets from (default: boot the ROM for 60 frames)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--also-envs", type=int, default=-1,
@@ -122,13 +133,25 @@ class ClockSampler:
 
 
 def build_rom(name: str) -> bytes:
+    """`name` is a synthetic ROM of pokegym_b200.tools.synth_rom.rom_catalog() or a path to a user-supplied .gb file
+    (BASELINE.json config 1: pokemon_red.gb; no ROM ships with the reference, so the default is synthetic)."""
     from pokegym_b200.tools import synth_rom
 
-    fn, kw = synth_rom.rom_catalog()[name]
-    return fn(**kw)
+    if name in synth_rom.rom_catalog():
+        fn, kw = synth_rom.rom_catalog()[name]
+        return fn(**kw)
+    return Path(name).read_bytes()
 
 
-def oracle_env_steps_per_s(rom: bytes, seconds: float, n_envs=None):
+def start_envs(h, state_path):
+    """Every env starts from the same point: the given PyBoy .state file, or the ROM booted for 60 frames."""
+    if state_path:
+        h.set_initial_template(h.add_state_template(Path(state_path).read_bytes()))
+    else:
+        h.tick(60, True)
+
+
+def oracle_env_steps_per_s(rom: bytes, seconds: float, n_envs=None, state_path=None):
     """CPU oracle (port of the reference path) on all host cores; returns (value, cores, sample description)."""
     import numpy as np
 
@@ -139,7 +162,7 @@ def oracle_env_steps_per_s(rom: bytes, seconds: float, n_envs=None):
     cores = os.cpu_count() or 1
     n = n_envs or max(cores * 4, 8)
     h = _capi.Handle(lib, n, rom)
-    h.tick(60, True)
+    start_envs(h, state_path)
     obs = np.zeros((n, _capi.OBS_BYTES), dtype=np.uint8)
     rew = np.zeros(n)
     done = np.zeros(n, dtype=np.uint8)
@@ -175,7 +198,7 @@ def run_reference(args):
 
     lib = _capi.GbEnvLib(g.build_oracle(), "oracle_")
     h = _capi.Handle(lib, n, rom)
-    h.tick(60, True)
+    start_envs(h, args.state)
     obs = np.zeros((n, _capi.OBS_BYTES), dtype=np.uint8)
     rew = np.zeros(n)
     done = np.zeros(n, dtype=np.uint8)
@@ -193,7 +216,7 @@ def run_reference(args):
         "impl": "reference", "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": n, "act_freq": 24, "rom": args.rom,
+        "config": {"workload": workload_name(args), "envs_per_step": n, "act_freq": 24, "rom": args.rom,
                    "note": "bounded sample: each step advances `envs_per_step` envs on the host cores"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{n} envs x {args.steps} env-steps on {cores} host threads (oracle port; PyBoy + ROM unavailable)"},
@@ -228,7 +251,7 @@ def main():
     E, K, W = args.envs_per_gpu, args.steps, max(args.warmup, 3)
     rom = build_rom(args.rom)
     h = _capi.Handle(lib, E, rom, device_id=local_rank)
-    h.tick(60, True)  # boot the synthetic game to its main loop; every env then starts from the same state
+    start_envs(h, args.state)  # every env starts from the same state and diverges through its actions
     rollout = torch.zeros((ROLLOUT_T, E, _capi.OBS_BYTES), dtype=torch.uint8, device=dev)
     reward = torch.zeros((ROLLOUT_T, E), dtype=torch.float64, device=dev)
     done = torch.zeros((ROLLOUT_T, E), dtype=torch.uint8, device=dev)
@@ -311,7 +334,7 @@ def main():
     line = {
         "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": E, "act_freq": 24, "rom": args.rom, "parallelism": f"env-sharded x{world}",
+        "config": {"workload": workload_name(args), "envs_per_gpu": E, "act_freq": 24, "rom": args.rom, "parallelism": f"env-sharded x{world}",
                    "l2_policy": f"working set {E * (16896 + 5760 + 23040 + 1152) / 1e6:.0f} MB of env state + obs per GPU exceeds the 126 MB L2; no explicit flush"},
         "frames_per_s": 24 * value,
         "emulated_instr_per_s": instr / (ms / 1000.0) * world,
@@ -336,7 +359,7 @@ def main():
             torch.cuda.empty_cache()
             E2 = args.also_envs
             h2 = _capi.Handle(lib, E2, rom, device_id=local_rank)
-            h2.tick(60, True)
+            start_envs(h2, args.state)
             ro2 = torch.zeros((4, E2, _capi.OBS_BYTES), dtype=torch.uint8, device=dev)
             rw2 = torch.zeros(E2, dtype=torch.float64, device=dev)
             dn2 = torch.zeros(E2, dtype=torch.uint8, device=dev)
@@ -357,7 +380,7 @@ def main():
         except Exception as e:
             line["large_batch"] = {"error": str(e)}
     try:
-        v, cores, sample = oracle_env_steps_per_s(rom, args.cpu_baseline_seconds)
+        v, cores, sample = oracle_env_steps_per_s(rom, args.cpu_baseline_seconds, state_path=args.state)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
     except Exception as e:  # the baseline is reported, never required for the GPU number
         line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
