@@ -10,9 +10,7 @@
 // env state lives in word-interleaved HBM arrays (gb_layout.cuh), and the main loop is organised
 // around LCD events so the 32 envs of a warp re-converge at every scanline boundary.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
+#include "gb_hd.h"
 #include "gb_layout.cuh"
 
 #define FLAG_Z 0x80u
@@ -61,6 +59,7 @@ struct Machine {
     uint32_t hdr;
     // statistics (n_cycles = clock delta + cyc_adj, see machine_store)
     uint32_t n_instr, n_cycles, cyc_adj, clock0;
+    int t_sync;  // k_run_frames: value of the interpreter's cycle countdown when clock / divc were last brought up to date
     // memory (pointers already offset to this env's lane inside its tile)
     uint8_t *memb;   // plain RAM, byte i at memb[((i >> 2) << 7) | (i & 3)]
     uint8_t *cramb;  // cart RAM, same addressing
@@ -122,6 +121,7 @@ __device__ inline void machine_load(Machine &m, const DevArrays &d, int tile, in
     m.n_cycles = 0;
     m.cyc_adj = 0;
     m.clock0 = m.clock;
+    m.t_sync = 0;
 }
 
 __device__ inline void machine_store(Machine &m, const DevArrays &d, int tile, int lane) {
@@ -391,7 +391,7 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
 
 // Out-of-line entry points of the renderer: inputs by value, so the caller's Machine stays in registers
 // and the (large) renderer body is kept out of the interpreter's hot loop.
-__device__ __noinline__ int render_line_out(uint8_t *memb, uint32_t *fb, uint32_t lcdc, uint32_t scroll, uint32_t pal, int ly_window, uint32_t y,
+__device__ GB_NOINLINE int render_line_out(uint8_t *memb, uint32_t *fb, uint32_t lcdc, uint32_t scroll, uint32_t pal, int ly_window, uint32_t y,
                                             uint32_t *line, uint32_t *keys, uint32_t ls) {
     Machine r;
     r.memb = memb; r.fb = fb;
@@ -401,7 +401,7 @@ __device__ __noinline__ int render_line_out(uint8_t *memb, uint32_t *fb, uint32_
     return r.ly_window;
 }
 
-__device__ __noinline__ void fill_framebuffer(uint32_t *fb, uint32_t fill) {
+__device__ GB_NOINLINE void fill_framebuffer(uint32_t *fb, uint32_t fill) {
     for (uint32_t k = 0; k < FB_WORDS; k++) fb[k << 5] = fill;
 }
 
@@ -476,8 +476,9 @@ __device__ __forceinline__ uint32_t timer_divider(uint32_t tac) {
     return (tac & 3) == 0 ? 1024u : (4u << ((tac & 3) * 2));  // 1024, 16, 64, 256
 }
 
-__device__ __forceinline__ void timer_tick(Machine &m, uint32_t cycles) {
-    m.divc += cycles;  // DIV = div + (divc >> 8), materialised on read / store
+// Timer.tick, TIMA half (PyBoy: one increment per tick at most).  The DIV half is `divc += cycles`, which the
+// interpreter applies lazily together with the LCD clock (DIV = div + (divc >> 8), materialised on read / store).
+__device__ __forceinline__ void timer_tick_tima(Machine &m, uint32_t cycles) {
     if (m.tmr & 0x04000000u) {  // TAC bit 2: timer enabled
         m.timac += cycles;
         uint32_t dv = timer_divider(M_TAC(m));
@@ -507,7 +508,7 @@ __device__ __forceinline__ int timer_cycles_to_interrupt(const Machine &m) {
 
 #define IO_NOT_A_REGISTER 0x100u
 // value of an IO register modelled outside the IO array, or IO_NOT_A_REGISTER
-__device__ __noinline__ uint32_t io_reg_read(uint32_t a, uint32_t lcd0 /* LCDC STAT LY LYC */, uint32_t scroll /* SCX SCY WX WY */,
+__device__ GB_NOINLINE uint32_t io_reg_read(uint32_t a, uint32_t lcd0 /* LCDC STAT LY LYC */, uint32_t scroll /* SCX SCY WX WY */,
                                              uint32_t pal_ie /* BGP OBP0 OBP1 IE */, uint32_t tim /* DIV TIMA TMA TAC */, uint32_t iflag) {
     switch (a) {
     case 0xFF04: return tim & 0xFF;
@@ -549,7 +550,7 @@ __device__ __forceinline__ uint32_t bus_read_full(Machine &m, uint32_t a) {  // 
     }
     return mem_rd(m, MEM_HI + (a - 0xFE00));  // OAM, 0xFEA0-0xFEFF, plain IO array bytes
 }
-__device__ __noinline__ uint32_t bus_read_slow(Machine &m, uint32_t a) { return bus_read_full(m, a); }
+__device__ GB_NOINLINE uint32_t bus_read_slow(Machine &m, uint32_t a) { return bus_read_full(m, a); }
 __device__ __forceinline__ uint32_t bus_read(Machine &m, uint32_t a) {  // wrapper kernels / debug access
     if (a < 0x8000) return __ldg(m.rom + (a < 0x4000 ? a : a + m.rom_off));
     if (a >= 0xC000 && a < 0xE000) return mem_rd(m, MEM_WRAM + (a - 0xC000));
@@ -557,7 +558,7 @@ __device__ __forceinline__ uint32_t bus_read(Machine &m, uint32_t a) {  // wrapp
 }
 
 // Everything a store can do besides hitting plain RAM: MBC3 registers, cart RAM, IO registers, OAM DMA.
-__device__ __noinline__ void bus_write_rare(Machine *mp, uint32_t a, uint32_t v) {
+__device__ GB_NOINLINE void bus_write_rare(Machine *mp, uint32_t a, uint32_t v) {
     Machine &m = *mp;
     if (a < 0x8000) {  // MBC3 registers
         if (a < 0x2000) {
@@ -623,9 +624,7 @@ __device__ __forceinline__ void bus_write_full(Machine &m, uint32_t a, uint32_t 
     if (a - 0xC000u < 0x3E00u) { mem_wr(m, MEM_WRAM + (a & 0x1FFF), v); return; }
     if ((a >= 0xFF80 && a != 0xFFFF) || (a >= 0xFE00 && a < 0xFF00)) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }
     if (a - 0x8000u < 0x2000u) { mem_wr(m, MEM_VRAM + (a - 0x8000), v); return; }
-    Machine t = m;  // rare: work on a scratch copy so that `m` keeps living in registers
-    bus_write_rare(&t, a, v);
-    m = t;
+    bus_write_rare(&m, a, v);
 }
 __device__ __forceinline__ void bus_write(Machine &m, uint32_t a, uint32_t v) {  // wrapper kernels / debug access
     v &= 0xFF;

@@ -3,13 +3,13 @@
 #include "gb_cpu.cuh"
 #include "gb_device.cuh"
 
-// 64-thread blocks, 10 per SM (96 registers): the same 20 resident warps per SM as 128 x 5, but a finer grain for the
-// block scheduler, so SMs differ by one block of two warps instead of four (+1 % at 4,096 and 32,768 envs)
+// 64-thread blocks; the register budget (64) lets 16 of them share an SM, i.e. 32 resident warps: the interpreter is a
+// chain of dependent instructions, so throughput below ~60k envs is set by how many warps the schedulers can rotate.
 #ifndef STEP_THREADS
 #define STEP_THREADS 64
 #endif
 #ifndef STEP_MIN_BLOCKS
-#define STEP_MIN_BLOCKS 10
+#define STEP_MIN_BLOCKS 16
 #endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
@@ -23,31 +23,31 @@ struct RunParams {
     int render_mode;  // 0: renderer disabled, 1: enabled on every frame, 2: enabled on the last frame only
     int release_frame;  // frame index at which the button is released (8 in the reference)
     int lanes;          // envs per warp (1..32): fewer lanes = more warps = more latency hiding
+    uint32_t bank_mask;  // rom_banks - 1 when the bank count is a power of two, else 0
     unsigned long long *counters;  // [0] instructions, [1] cycles, [2] frames, [3] faults
 };
 
-// One thread per env, one warp per 32-env tile.  Runs `n_frames` whole frames without returning to the
-// host (pyboy_binding.run_action_on_emulator :71-91).  The loop is organised around LCD events: the
-// inner do-while interprets instructions until this env's LCD clock reaches its next mode change, the
-// outer body performs the mode change (scanline parameters, rendering, LY/STAT/interrupt flags).  All
-// envs see the same number of LCD events per frame, so the warp re-converges 442 times a frame and
-// the scanline renderer runs with all 32 lanes active.
-__global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(RunParams p) {
-    __shared__ uint32_t s_line[FB_LINE_WORDS * STEP_THREADS];
-    __shared__ uint32_t s_keys[10 * STEP_THREADS];
-    const int tid = threadIdx.x;
-    const int warp = (blockIdx.x * STEP_THREADS + tid) >> 5, wl = tid & 31;
-    if (wl >= p.lanes) return;  // partial-warp mode: only the first `lanes` threads of each warp carry an env
-    const int env = warp * p.lanes + wl;
-    if (env >= p.d.n_envs) return;
-    const int tile = env >> 5, lane = env & 31;
-    uint32_t *line = s_line + tid, *keys = s_keys + tid;
-    const uint32_t ls = STEP_THREADS;
-
+// Per-env slot in shared memory: the machine plus the four words the on-the-fly decoder returns its descriptor in.
+// The slot stride is an odd number of 8-byte units, so the same field of 32 consecutive slots falls into 16 banks
+// (two-way conflicts, on cold paths only: the hot state is in registers).  The renderer's line buffer and sprite sort
+// keys follow as [word][slot] arrays (conflict-free).
+struct EnvSlot {
     Machine m;
-    machine_load(m, p.d, tile, lane);
-    const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
+    uint32_t scratch[4];
+};
+#define ENV_SLOT_STRIDE ((sizeof(EnvSlot) + 7) / 8 * 8 + ((((sizeof(EnvSlot) + 7) / 8) & 1) ? 0 : 8))
+#define ENV_SMEM_BYTES(nslots) ((size_t)(nslots) * (ENV_SLOT_STRIDE + (FB_LINE_WORDS + 10) * 4))
 
+// The frame loop of one env (pyboy_binding.run_action_on_emulator :71-91 around Motherboard.tick).  It is organised
+// around LCD events: cpu_run_to_event interprets until this env's LCD clock reaches its next mode change, then the
+// mode change is performed (scanline parameters, rendering, LY/STAT/interrupt flags).  All envs see the same number
+// of LCD events per frame, so a warp re-converges 442 times a frame and the scanline renderer runs with every lane.
+__device__ __forceinline__ void run_frames_env(EnvSlot &slot, const RunParams &p, int button, uint32_t *line, uint32_t *keys, uint32_t ls) {
+    Machine &m = slot.m;
+    RunCtx cx;
+    cx.rom_dec = p.d.rom_dec;
+    cx.bank_mask = p.bank_mask;
+    uint32_t bcde = m.bcde, hlaf = m.hlaf, sp = m.sp, pc = m.pc, rom_off = m.rom_off, n_instr = 0;
     for (int frame = 0; frame < p.n_frames; frame++) {
         // PyBoy.tick applies queued inputs before Motherboard.tick
         if (button >= 0) {
@@ -82,35 +82,35 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
                 const int a = (int)(m.target - m.clock);
                 if (a > 0) { m.divc += a; m.clock += a; }
             } else {
-                bool event;
-                do {
-                    DeferredWrites dw;
-                    uint32_t cycles = cpu_step(m, p.d.rom_dec, dw);
-                    // one divergent region for everything that is not plain register work: stores, HALT, a running TIMA
-                    if (dw.n | m.halted | (m.tmr & 0x04000000u)) {
-                        cpu_commit_writes(m, dw);
-                        if (m.halted | (m.tmr & 0x04000000u)) {
-                            if (m.halted) {  // fast-forward to the next LCD mode change / timer overflow
-                                int a = (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m);
-                                int c = a < b ? a : b;
-                                cycles = c < 0 ? 0 : (uint32_t)c;
-                            }
-                            timer_tick(m, cycles);
-                        } else {
-                            m.divc += cycles;
-                        }
-                    } else {
-                        m.divc += cycles;  // Timer.tick with the timer stopped: only DIV advances (kept lazily)
-                    }
-                    m.clock += cycles;
-                    event = m.clock >= ((m.lcdc & 0x80) ? m.target : FRAME_CYCLES);
-                } while (!event);
+                cpu_run_to_event(m, cx, bcde, hlaf, sp, pc, rom_off, n_instr, slot.scratch);
             }
             lcd_event(m, line, keys, ls);
             done = m.frame_done;
             m.frame_done = 0;
         }
     }
+    m.bcde = bcde; m.hlaf = hlaf; m.sp = sp; m.pc = pc;
+    m.n_instr += n_instr;
+}
+
+// One thread per env; `lanes` envs per warp (the first `lanes` threads of each warp carry one; 32 = a full tile per
+// warp).  Runs `n_frames` whole frames without returning to the host.
+#if !defined(GB_HOSTSIM)
+extern __shared__ unsigned long long s_env_slots[];
+__global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(RunParams p) {
+    const int tid = threadIdx.x;
+    const int warp = (blockIdx.x * STEP_THREADS + tid) >> 5, wl = tid & 31;
+    if (wl >= p.lanes) return;  // partial-warp mode: only the first `lanes` threads of each warp carry an env
+    const int env = warp * p.lanes + wl;
+    if (env >= p.d.n_envs) return;
+    const int tile = env >> 5, lane = env & 31;
+    const uint32_t nslots = (STEP_THREADS / 32) * p.lanes, si = (tid >> 5) * p.lanes + wl;
+    EnvSlot &slot = *(EnvSlot *)((char *)s_env_slots + (size_t)si * ENV_SLOT_STRIDE);
+    uint32_t *const line = (uint32_t *)((char *)s_env_slots + (size_t)nslots * ENV_SLOT_STRIDE) + si, *const keys = line + FB_LINE_WORDS * nslots;
+    Machine &m = slot.m;
+    machine_load(m, p.d, tile, lane);
+    const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
+    run_frames_env(slot, p, button, line, keys, nslots);
     machine_store(m, p.d, tile, lane);
     if (p.counters) {
         atomicAdd(&p.counters[0], (unsigned long long)m.n_instr);
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
         atomicAdd(&p.counters[2], (unsigned long long)p.n_frames);
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Canonical per-env image <-> interleaved arrays.  image word j of env e lives at:

@@ -8,6 +8,7 @@
 // sequential copy inside one env stays inside one 32-byte sector.
 #pragma once
 #include <stdint.h>
+#include "gb_hd.h"
 
 #define GB_TILE 32
 
@@ -67,7 +68,7 @@ struct DevArrays {
     uint32_t *lp;    // [tiles][LP_WORDS][32]
     uint32_t *regs;  // [tiles][R_WORDS][32]
     const uint8_t *rom;
-    const uint2 *rom_dec;  // pre-decoded ROM: one 8-byte instruction descriptor per ROM offset (gb_predecode.h)
+    const uint4 *rom_dec;  // pre-decoded ROM: one 16-byte control word per ROM offset (gb_predecode.h)
     uint32_t rom_banks;
     int n_envs;
     int n_tiles;

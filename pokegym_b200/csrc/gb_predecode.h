@@ -1,117 +1,350 @@
 // gb_predecode.h -- pre-decoded instruction descriptors (host + device).
 //
-// The cartridge ROM is shared by every env and never changes, so it is decoded ONCE per handle: for each
-// ROM offset the library stores an 8-byte descriptor {handler, register fields, length, cycle counts,
-// immediate, precomputed relative-jump target}.  The interpreter then fetches one 64-bit word per
-// instruction from this L2-resident table and jumps straight to a specialised handler -- no opcode
-// bit-field decoding, operand fetching or length/cycle computation on the hot path.  Code executed from
-// RAM (the HRAM OAM-DMA stub) and the last bytes of each 16 KiB bank are decoded on the fly from the same
-// per-opcode base table.
+// The cartridge ROM is shared by every env and never changes, so it is decoded ONCE per handle: for each ROM
+// offset the library stores a 16-byte descriptor and the interpreter fetches one 128-bit word per instruction from
+// this L2-resident table.  The descriptor is not a compressed opcode: it is the control word of a small uniform
+// datapath (gb_cpu.cuh) --
+//
+//     operand fetch  ->  handler (one of 15 short bodies; plain moves need none)  ->  register write-back  ->  deferred bus write
+//
+// whose operand-fetch and write-back stages are the same straight-line code for every instruction.  The eight
+// 8-bit SM83 registers live in two packed words (bcde = C|B<<8|E<<16|D<<24, hlaf = L|H<<8|A<<16|F<<24), i.e.
+// bytes 0..7 of a PRMT source pair, so "which register" is a PRMT selector and the descriptor carries the selectors
+// ready-made:
+//
+//   x: handler | cycles << 8 | ex << 16 | op << 24
+//        cycles  T-cycles (condition false / unconditional)
+//        ex      low nibble: extra T-cycles when a conditional branch is taken; bits 4 / 7: flag value the
+//                condition expects (compared under the mask in `op`)
+//        op      handler operand: ALU op, INC/DEC select, signed +-1 for HL+/HL-/INC rr/DEC rr, condition mask
+//                (0 = always, 0x80 = Z, 0x10 = C), rotate kind, POP low-byte mask, or the opcode (H_RARE)
+//   y: imm16 | next_pc << 16      imm16: immediate, or a ready-made value -- the JR/JP/CALL/RST target, 0xFF00|n
+//                                 for LDH, the BIT mask, the RES/SET and/or masks
+//   z: sel_lo | sel_hi << 16      write-back: bcde = prmt(bcde, rv, sel_lo); hlaf = prmt(hlaf, rv, sel_hi), where rv is
+//                                 the handler's 32-bit result (0x3210 = keep; nibble k = 4 + j puts result byte j
+//                                 into register byte k).  8-bit results travel as res | new_F << 8, so "ADD writes
+//                                 A and F", "CP writes F only" and "INC B writes B and F" differ only in selectors.
+//   w: srcsel | flags << 4 | asel << 16
+//        srcsel  PRMT nibble of the 8-bit source register (byte 0..7 of bcde:hlaf)
+//        asel    PRMT selector of the 16-bit address / pair operand (BC 0x10, DE 0x32, HL 0x54, AF-for-PUSH 0x67)
+//        flags   PDF_* below
+//
+// Code executed from RAM (the HRAM OAM-DMA stub) and instructions whose operand bytes straddle a 16 KiB bank
+// boundary are decoded on the fly from the same per-opcode base table (pd_finish).
 #pragma once
 #include <stdint.h>
 
-// descriptor word 0:  handler | taken_extra << 6 | Y << 8 | Z << 16 | cycles << 24   (byte-aligned: one PRMT / shift each)
-//   Y  opcode bits 3-5: destination register / ALU op / bit index / condition (H_RARE: the whole opcode byte)
-//   Z  opcode bits 0-2: source register
-//   cycles  T-cycles, condition false / unconditional;  taken_extra  (T-cycles when the condition holds - cycles) / 4
-// descriptor word 1:  imm16 | next_pc << 16   (H_JR: the branch target instead of imm16; CB page: opcode bits 6-7)
-#define PD_H(x) ((x) & 63u)
-#define PD_TAKEN_EXTRA(x) ((((x) >> 6) & 3u) * 4u)
-#if defined(__CUDA_ARCH__)
-#define PD_Y(x) __byte_perm((x), 0, 0x4441)
-#define PD_Z(x) __byte_perm((x), 0, 0x4442)
-#else
-#define PD_Y(x) (((x) >> 8) & 0xFFu)
-#define PD_Z(x) (((x) >> 16) & 0xFFu)
-#endif
-#define PD_CYC(x) ((x) >> 24)
-
 enum {
     H_SLOW = 0,  // not pre-decodable here (instruction straddles a bank boundary): decode on the fly
-    H_NOP, H_LD_R_R, H_LD_R_HL, H_LD_HL_R, H_LD_R_N, H_LD_HL_N, H_LD_A_RP, H_LD_RP_A,
-    H_LDH_N_A, H_LDH_A_N, H_LD_C_A, H_LD_A_C, H_LD_NN_A, H_LD_A_NN,
-    H_ALU_R, H_ALU_HL, H_ALU_N, H_INCDEC_R, H_INCDEC_HL, H_LD_RP_NN, H_INCDEC_RP, H_ADD_HL,
-    H_JR, H_JP, H_CALL, H_RET, H_RETI, H_RST, H_PUSH, H_POP, H_CB_R, H_CB_HL, H_ROT_A, H_RARE,
+    H_MOV,       // rv = v : every 8-bit load / store and LD rr,nn (the selectors / PDF_WR say where it goes); NOP
+    H_HLI,       // rv = (pair + op) | v << 16 : LD A,(HL+-)  LD (HL+-),A  INC rr  DEC rr
+    H_ARITH,     // ADD ADC SUB SBC CP on A with v   (op bit 0: carry in; ex = 0xFF for the subtractions)
+    H_LOGIC,     // AND XOR OR on A with v           (ex = mask of a & v, op = mask of a ^ v)
+    H_INCDEC,    // INC / DEC of v (register or (HL)): op = 1 / 0xFF, ex = 0 / N|H
+    H_ADD_HL,    // ADD HL,rr (BC DE HL)
+    H_JUMP,      // JR / JP, conditional or not (target ready in imm16)
+    H_CALL,      // CALL cc / CALL / RST
+    H_RET,       // RET cc / RET / RETI
+    H_PUSH,
+    H_POP,
+    H_ROT,       // CB rotates / shifts / SWAP on v, and RLCA RRCA RLA RRA (op bit 3: Z forced clear)
+    H_BIT,       // BIT b,v
+    H_RESSET,    // RES / SET b,v
+    H_RARE,      // everything else, by opcode
     H__COUNT
 };
 
-// `len` travels in bits 28-29 of the BASE entry only (pd_split_len strips it); cycles <= 24 needs bits 24-28
-static inline uint32_t pd_make(uint32_t h, uint32_t y, uint32_t z, uint32_t len, uint32_t cyc, uint32_t cyc2, uint32_t op) {
-    if (h == H_RARE) y = op;
-    return h | (((cyc2 - cyc) / 4) << 6) | (y << 8) | (z << 16) | (cyc << 24) | (len << 29);
+#define PDF_IMM 0x0010u   // v = imm16
+#define PDF_RD 0x0020u    // v = bus[addr]
+#define PDF_RD16 0x0040u  // v |= bus[addr + 1] << 8
+#define PDF_AIMM 0x0080u  // addr = imm16 (else the pair selected by asel)
+#define PDF_ASP 0x0100u   // addr = SP
+#define PDF_WR 0x0200u    // one deferred byte store of the handler's `wv` at addr
+#define PDF_RETI 0x0400u  // RETI: IME = 1
+
+#define PD_H(x) ((x) & 0xFFu)
+#define PD_CYC(x) (((x) >> 8) & 0xFFu)
+#define PD_EX(x) (((x) >> 16) & 0xFFu)
+#define PD_OP(x) ((x) >> 24)
+
+#if defined(__VECTOR_TYPES_H__)  // cuda_runtime.h (or the host-simulation shim) has defined uint4
+typedef uint4 pd_desc_t;
+#else
+struct pd_desc_t { uint32_t x, y, z, w; };
+#endif
+
+// base-table entries keep instance-independent fields; y = constant imm | len << 16 | immediate kind << 24
+enum { PDK_CONST = 0, PDK_IMM8, PDK_IMM16, PDK_JR, PDK_LDH };
+#define PD_BASE_LEN(y) (((y) >> 16) & 3u)
+#define PD_BASE_KIND(y) ((y) >> 24)
+
+// register index of the opcode encoding (B C D E H L - A) -> byte number inside bcde:hlaf
+static inline uint32_t pd_reg_byte(uint32_t idx) { return ((idx & 4) ? 4u : 0u) + ((idx ^ 1u) & 3u); }
+
+struct pd_builder {
+    uint32_t h, cyc, ex, op, imm, len, kind, sel_lo, sel_hi, srcsel, flags, asel;
+};
+static inline void pd_b_init(pd_builder *b, uint32_t h, uint32_t len, uint32_t cyc) {
+    b->h = h; b->cyc = cyc; b->ex = 0; b->op = 0; b->imm = 0; b->len = len; b->kind = PDK_CONST;
+    b->sel_lo = 0x3210; b->sel_hi = 0x3210; b->srcsel = 0; b->flags = 0; b->asel = 0x5454;
 }
-#define PD_BASE_LEN(x) ((x) >> 29)
-#define PD_BASE_WORD0(x) ((x) & 0x1FFFFFFFu)
+// result byte j of rv -> register byte k (0..7)
+static inline void pd_b_write(pd_builder *b, uint32_t k, uint32_t j) {
+    uint32_t *sel = k < 4 ? &b->sel_lo : &b->sel_hi;
+    uint32_t sh = (k & 3) * 4;
+    *sel = (*sel & ~(0xFu << sh)) | ((4u + j) << sh);
+}
+static inline void pd_b_src_reg(pd_builder *b, uint32_t idx) { b->srcsel = pd_reg_byte(idx); }
+static inline void pd_b_pair(pd_builder *b, uint32_t p) {  // BC DE HL as the address / 16-bit operand
+    static const uint32_t s[3] = {0x1010, 0x3232, 0x5454};
+    b->asel = s[p];
+}
+static inline void pd_b_write_pair(pd_builder *b, uint32_t p) {  // rv bytes 0,1 -> pair p (BC DE HL)
+    pd_b_write(b, p * 2, 0);
+    pd_b_write(b, p * 2 + 1, 1);
+}
+static inline pd_desc_t pd_b_done(const pd_builder *b) {
+    pd_desc_t d;
+    d.x = b->h | (b->cyc << 8) | (b->ex << 16) | (b->op << 24);
+    d.y = (b->imm & 0xFFFFu) | (b->len << 16) | (b->kind << 24);
+    d.z = b->sel_lo | (b->sel_hi << 16);
+    d.w = (b->srcsel & 0xFu) | (b->flags & 0xFFF0u) | (b->asel << 16);
+    return d;
+}
+
+// condition cc (NZ Z NC C) -> mask in op, expected flag value in ex
+static inline void pd_b_cond(pd_builder *b, uint32_t cc, uint32_t taken_extra) {
+    uint32_t mask = (cc & 2) ? 0x10u : 0x80u;
+    b->op = mask;
+    b->ex = taken_extra | ((cc & 1) ? mask : 0u);
+}
+
+// ALU group y = ADD ADC SUB SBC AND XOR OR CP
+static inline void pd_b_alu(pd_builder *b, uint32_t y) {
+    if (y >= 4 && y <= 6) {
+        b->h = H_LOGIC;
+        b->ex = y == 5 ? 0u : 0xFFu;
+        b->op = y == 4 ? 0u : 0xFFu;
+    } else {
+        b->h = H_ARITH;
+        b->ex = (y == 2 || y == 3 || y == 7) ? 0xFFu : 0u;
+        b->op = (y == 1 || y == 3) ? 1u : 0u;
+    }
+}
 
 // Per-opcode base descriptors (256 base + 256 CB page).  Cycle counts: the pastraiser table PyBoy 1.6 uses.
-// For conditional control flow the Y field holds the condition: 0 = always, 4..7 = NZ Z NC C.
-static inline void pd_build_base(uint32_t *t) {
-    for (uint32_t op = 0; op < 256; op++) {
-        uint32_t x = op >> 6, y = (op >> 3) & 7, z = op & 7, p = y >> 1, q = y & 1;
-        uint32_t d = pd_make(H_RARE, y, z, 1, 4, 4, op);
+static inline void pd_build_base(pd_desc_t *t) {
+    for (uint32_t opc = 0; opc < 256; opc++) {
+        const uint32_t x = opc >> 6, y = (opc >> 3) & 7, z = opc & 7, p = y >> 1, q = y & 1;
+        pd_builder b;
+        pd_b_init(&b, H_RARE, 1, 4);
+        b.op = opc;
         if (x == 1) {
-            if (op != 0x76) d = z == 6 ? pd_make(H_LD_R_HL, y, z, 1, 8, 8, op) : y == 6 ? pd_make(H_LD_HL_R, y, z, 1, 8, 8, op) : pd_make(H_LD_R_R, y, z, 1, 4, 4, op);
-        } else if (x == 2) {
-            d = z == 6 ? pd_make(H_ALU_HL, y, z, 1, 8, 8, op) : pd_make(H_ALU_R, y, z, 1, 4, 4, op);
+            if (opc != 0x76) {  // LD r,r' / LD r,(HL) / LD (HL),r
+                pd_b_init(&b, H_MOV, 1, (y == 6 || z == 6) ? 8 : 4);
+                if (z == 6) b.flags |= PDF_RD;
+                else pd_b_src_reg(&b, z);
+                if (y == 6) b.flags |= PDF_WR;
+                else pd_b_write(&b, pd_reg_byte(y), 0);
+            }
+        } else if (x == 2) {  // ALU A,r / ALU A,(HL)
+            pd_b_init(&b, H_ARITH, 1, z == 6 ? 8 : 4);
+            pd_b_alu(&b, y);
+            if (z == 6) b.flags |= PDF_RD;
+            else pd_b_src_reg(&b, z);
+            if (y != 7) pd_b_write(&b, 6, 0);  // CP keeps A
+            pd_b_write(&b, 7, 1);
         } else if (x == 0) {
             switch (z) {
             case 0:
-                if (y == 0) d = pd_make(H_NOP, 0, 0, 1, 4, 4, op);
-                else if (y == 3) d = pd_make(H_JR, 0, 0, 2, 12, 12, op);
-                else if (y >= 4) d = pd_make(H_JR, y, 0, 2, 8, 12, op);
-                else if (y == 1) d = pd_make(H_RARE, y, z, 3, 20, 20, op);  // LD (nn),SP
-                else if (y == 2) d = pd_make(H_RARE, y, z, 2, 4, 4, op);    // STOP skips a byte
+                if (y == 0) {
+                    pd_b_init(&b, H_MOV, 1, 4);  // NOP: a move that writes nothing
+                } else if (y == 1) {
+                    b.len = 3; b.cyc = 20; b.kind = PDK_IMM16;  // LD (nn),SP (rare)
+                } else if (y == 2) {
+                    b.len = 2;  // STOP skips a byte (rare)
+                } else {
+                    pd_b_init(&b, H_JUMP, 2, y == 3 ? 12 : 8);
+                    b.kind = PDK_JR;
+                    if (y >= 4) pd_b_cond(&b, y & 3, 4);
+                }
                 break;
-            case 1: d = q == 0 ? pd_make(H_LD_RP_NN, y, z, 3, 12, 12, op) : pd_make(H_ADD_HL, y, z, 1, 8, 8, op); break;
-            case 2: d = q == 0 ? pd_make(H_LD_RP_A, y, z, 1, 8, 8, op) : pd_make(H_LD_A_RP, y, z, 1, 8, 8, op); break;
-            case 3: d = pd_make(H_INCDEC_RP, y, z, 1, 8, 8, op); break;
+            case 1:
+                if (q == 0) {
+                    if (p == 3) { b.len = 3; b.cyc = 12; b.kind = PDK_IMM16; }  // LD SP,nn (rare)
+                    else {
+                        pd_b_init(&b, H_MOV, 3, 12);
+                        b.kind = PDK_IMM16; b.flags |= PDF_IMM;
+                        pd_b_write_pair(&b, p);
+                    }
+                } else {
+                    if (p == 3) { b.cyc = 8; }  // ADD HL,SP (rare)
+                    else {
+                        pd_b_init(&b, H_ADD_HL, 1, 8);
+                        pd_b_pair(&b, p);
+                        pd_b_write(&b, 4, 0); pd_b_write(&b, 5, 1); pd_b_write(&b, 7, 3);
+                    }
+                }
+                break;
+            case 2: {  // LD (BC/DE/HL+/HL-),A and LD A,(BC/DE/HL+/HL-)
+                pd_b_init(&b, p < 2 ? H_MOV : H_HLI, 1, 8);
+                pd_b_pair(&b, p < 2 ? p : 2);
+                if (p >= 2) b.op = p == 2 ? 1u : 0xFFu;
+                if (q == 0) {
+                    b.srcsel = 6; b.flags |= PDF_WR;
+                    if (p >= 2) { pd_b_write(&b, 4, 0); pd_b_write(&b, 5, 1); }
+                } else {
+                    b.flags |= PDF_RD;
+                    if (p >= 2) { pd_b_write(&b, 4, 0); pd_b_write(&b, 5, 1); pd_b_write(&b, 6, 2); }
+                    else pd_b_write(&b, 6, 0);
+                }
+                break;
+            }
+            case 3:
+                if (p == 3) { b.cyc = 8; }  // INC SP / DEC SP (rare)
+                else {
+                    pd_b_init(&b, H_HLI, 1, 8);
+                    pd_b_pair(&b, p);
+                    b.op = q ? 0xFFu : 1u;
+                    pd_b_write_pair(&b, p);
+                }
+                break;
             case 4:
-            case 5: d = y == 6 ? pd_make(H_INCDEC_HL, y, z, 1, 12, 12, op) : pd_make(H_INCDEC_R, y, z, 1, 4, 4, op); break;
-            case 6: d = y == 6 ? pd_make(H_LD_HL_N, y, z, 2, 12, 12, op) : pd_make(H_LD_R_N, y, z, 2, 8, 8, op); break;
+            case 5:
+                pd_b_init(&b, H_INCDEC, 1, y == 6 ? 12 : 4);
+                b.op = (z & 1) ? 0xFFu : 1u;
+                b.ex = (z & 1) ? 0x60u : 0u;
+                if (y == 6) b.flags |= PDF_RD | PDF_WR;
+                else { pd_b_src_reg(&b, y); pd_b_write(&b, pd_reg_byte(y), 0); }
+                pd_b_write(&b, 7, 1);
+                break;
+            case 6:
+                pd_b_init(&b, H_MOV, 2, y == 6 ? 12 : 8);
+                b.kind = PDK_IMM8; b.flags |= PDF_IMM;
+                if (y == 6) b.flags |= PDF_WR;
+                else pd_b_write(&b, pd_reg_byte(y), 0);
+                break;
             default:
-                if (y < 4) d = pd_make(H_ROT_A, y, z, 1, 4, 4, op);  // RLCA RRCA RLA RRA
+                if (y < 4) {  // RLCA RRCA RLA RRA: the CB rotate of A with Z forced clear
+                    pd_b_init(&b, H_ROT, 1, 4);
+                    b.op = y | 8u; b.srcsel = 6;
+                    pd_b_write(&b, 6, 0); pd_b_write(&b, 7, 1);
+                }
                 break;  // DAA CPL SCF CCF: rare
             }
         } else {
             switch (z) {
             case 0:
-                if (y < 4) d = pd_make(H_RET, 4 + y, 0, 1, 8, 20, op);
-                else if (y == 4) d = pd_make(H_LDH_N_A, y, z, 2, 12, 12, op);
-                else if (y == 6) d = pd_make(H_LDH_A_N, y, z, 2, 12, 12, op);
-                else if (y == 5) d = pd_make(H_RARE, y, z, 2, 16, 16, op);  // ADD SP,e
-                else d = pd_make(H_RARE, y, z, 2, 12, 12, op);              // LD HL,SP+e
+                if (y < 4) {
+                    pd_b_init(&b, H_RET, 1, 8);
+                    b.flags |= PDF_RD | PDF_RD16 | PDF_ASP;
+                    pd_b_cond(&b, y, 12);
+                } else if (y == 4 || y == 6) {  // LDH (n),A / LDH A,(n)
+                    pd_b_init(&b, H_MOV, 2, 12);
+                    b.kind = PDK_LDH; b.flags |= PDF_AIMM;
+                    if (y == 4) { b.srcsel = 6; b.flags |= PDF_WR; }
+                    else { b.flags |= PDF_RD; pd_b_write(&b, 6, 0); }
+                } else {
+                    b.len = 2; b.cyc = y == 5 ? 16 : 12; b.kind = PDK_IMM8;  // ADD SP,e / LD HL,SP+e (rare)
+                }
                 break;
             case 1:
-                if (q == 0) d = pd_make(H_POP, y, z, 1, 12, 12, op);
-                else if (p == 0) d = pd_make(H_RET, 0, 0, 1, 16, 16, op);
-                else if (p == 1) d = pd_make(H_RETI, 0, 0, 1, 16, 16, op);
-                else if (p == 3) d = pd_make(H_RARE, y, z, 1, 8, 8, op);  // LD SP,HL
+                if (q == 0) {
+                    pd_b_init(&b, H_POP, 1, 12);
+                    b.flags |= PDF_RD | PDF_RD16 | PDF_ASP;
+                    b.op = p == 3 ? 0xF0u : 0xFFu;
+                    if (p == 3) { pd_b_write(&b, 6, 1); pd_b_write(&b, 7, 0); }
+                    else pd_b_write_pair(&b, p);
+                } else if (p < 2) {
+                    pd_b_init(&b, H_RET, 1, 16);
+                    b.flags |= PDF_RD | PDF_RD16 | PDF_ASP | (p == 1 ? PDF_RETI : 0);
+                } else if (p == 3) {
+                    b.cyc = 8;  // LD SP,HL (rare)
+                }
                 break;  // JP HL: rare, 4 cycles
             case 2:
-                if (y < 4) d = pd_make(H_JP, 4 + y, 0, 3, 12, 16, op);
-                else if (y == 4) d = pd_make(H_LD_C_A, y, z, 1, 8, 8, op);
-                else if (y == 5) d = pd_make(H_LD_NN_A, y, z, 3, 16, 16, op);
-                else if (y == 6) d = pd_make(H_LD_A_C, y, z, 1, 8, 8, op);
-                else d = pd_make(H_LD_A_NN, y, z, 3, 16, 16, op);
+                if (y < 4) {
+                    pd_b_init(&b, H_JUMP, 3, 12);
+                    b.kind = PDK_IMM16;
+                    pd_b_cond(&b, y, 4);
+                } else if (y == 4 || y == 6) {
+                    b.cyc = 8;  // LD (FF00+C),A / LD A,(FF00+C) (rare handler: the address needs C at run time)
+                } else {  // LD (nn),A / LD A,(nn)
+                    pd_b_init(&b, H_MOV, 3, 16);
+                    b.kind = PDK_IMM16; b.flags |= PDF_AIMM;
+                    if (y == 5) { b.srcsel = 6; b.flags |= PDF_WR; }
+                    else { b.flags |= PDF_RD; pd_b_write(&b, 6, 0); }
+                }
                 break;
             case 3:
-                if (y == 0) d = pd_make(H_JP, 0, 0, 3, 16, 16, op);
+                if (y == 0) { pd_b_init(&b, H_JUMP, 3, 16); b.kind = PDK_IMM16; }
                 break;  // CB prefix (own page), DI, EI, illegal: rare
             case 4:
-                if (y < 4) d = pd_make(H_CALL, 4 + y, 0, 3, 12, 24, op);
+                if (y < 4) {
+                    pd_b_init(&b, H_CALL, 3, 12);
+                    b.kind = PDK_IMM16;
+                    pd_b_cond(&b, y, 12);
+                }
                 break;
             case 5:
-                if (q == 0) d = pd_make(H_PUSH, y, z, 1, 16, 16, op);
-                else if (p == 0) d = pd_make(H_CALL, 0, 0, 3, 24, 24, op);
+                if (q == 0) {
+                    pd_b_init(&b, H_PUSH, 1, 16);
+                    if (p == 3) b.asel = 0x6767;  // F low, A high
+                    else pd_b_pair(&b, p);
+                } else if (p == 0) {
+                    pd_b_init(&b, H_CALL, 3, 24);
+                    b.kind = PDK_IMM16;
+                }
                 break;
-            case 6: d = pd_make(H_ALU_N, y, z, 2, 8, 8, op); break;
-            default: d = pd_make(H_RST, y, z, 1, 16, 16, op); break;
+            case 6:
+                pd_b_init(&b, H_ARITH, 2, 8);
+                pd_b_alu(&b, y);
+                b.kind = PDK_IMM8; b.flags |= PDF_IMM;
+                if (y != 7) pd_b_write(&b, 6, 0);
+                pd_b_write(&b, 7, 1);
+                break;
+            default:  // RST: a CALL to a constant
+                pd_b_init(&b, H_CALL, 1, 16);
+                b.imm = y * 8;
+                break;
             }
         }
-        t[op] = d;
+        t[opc] = pd_b_done(&b);
     }
-    for (uint32_t op = 0; op < 256; op++) {
-        uint32_t y = (op >> 3) & 7, z = op & 7;
-        t[256 + op] = z == 6 ? pd_make(H_CB_HL, y, z, 2, 16, 16, op) : pd_make(H_CB_R, y, z, 2, 8, 8, op);
+    for (uint32_t opc = 0; opc < 256; opc++) {
+        const uint32_t x = opc >> 6, y = (opc >> 3) & 7, z = opc & 7;
+        pd_builder b;
+        pd_b_init(&b, x == 0 ? H_ROT : x == 1 ? H_BIT : H_RESSET, 2, z == 6 ? 16 : 8);
+        if (z == 6) b.flags |= PDF_RD | (x == 1 ? 0 : PDF_WR);
+        else pd_b_src_reg(&b, z);
+        if (x == 0) {
+            b.op = y;
+            pd_b_write(&b, 7, 1);
+        } else if (x == 1) {
+            b.imm = 1u << y;
+            pd_b_write(&b, 7, 1);
+        } else {
+            b.imm = x == 2 ? (0xFFu & ~(1u << y)) : (0xFFu | ((1u << y) << 8));  // and mask | or mask << 8
+        }
+        if (x != 1 && z != 6) pd_b_write(&b, pd_reg_byte(z), 0);
+        t[256 + opc] = pd_b_done(&b);
     }
+}
+
+// instance fields: ins = opcode | op1 << 8 | op2 << 16 at address pc, b = its base entry
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline pd_desc_t pd_finish(pd_desc_t b, uint32_t ins, uint32_t pc) {
+    const uint32_t imm16 = (ins >> 8) & 0xFFFFu, imm8 = imm16 & 0xFFu, len = PD_BASE_LEN(b.y);
+    uint32_t imm = b.y & 0xFFFFu;
+    switch (PD_BASE_KIND(b.y)) {
+    case PDK_IMM8: imm = imm8; break;
+    case PDK_IMM16: imm = imm16; break;
+    case PDK_JR: imm = (pc + 2 + ((imm8 ^ 0x80u) - 0x80u)) & 0xFFFFu; break;
+    case PDK_LDH: imm = 0xFF00u | imm8; break;
+    default: break;
+    }
+    b.y = imm | (((pc + len) & 0xFFFFu) << 16);
+    return b;
 }
