@@ -59,6 +59,7 @@ struct Machine {
     uint32_t hdr;
     // statistics (n_cycles = clock delta + cyc_adj, see machine_store)
     uint32_t n_instr, n_cycles, cyc_adj, clock0;
+    uint32_t lazy;  // k_run_frames: soft LCD events may be applied late (set by lcd_deadline)
     int t_sync;  // k_run_frames: value of the interpreter's cycle countdown when clock / divc were last brought up to date
     // memory (pointers already offset to this env's lane inside its tile)
     uint8_t *memb;   // plain RAM, byte i at memb[((i >> 2) << 7) | (i & 3)]
@@ -67,6 +68,9 @@ struct Machine {
     uint2 *lp;       // scanline y at lp[y * 32]
     const uint8_t *rom;
     uint32_t rom_banks;
+    // k_run_frames: this env's renderer scratch in shared memory (10-word line buffer and 10 sprite sort keys, stride rls)
+    uint32_t rls;
+    uint32_t *rline, *rkeys;
 };
 
 // ------------------------------------------------------------------------------- state load/store
@@ -122,6 +126,7 @@ __device__ inline void machine_load(Machine &m, const DevArrays &d, int tile, in
     m.cyc_adj = 0;
     m.clock0 = m.clock;
     m.t_sync = 0;
+    m.lazy = 0;
 }
 
 __device__ inline void machine_store(Machine &m, const DevArrays &d, int tile, int lane) {
@@ -413,16 +418,24 @@ __device__ __forceinline__ void lcd_blank_screen(Machine &m) {
 }
 
 // LCD.tick after `clock` has been advanced and found >= target (LCD on) or >= FRAME_CYCLES (LCD off).
-__device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uint32_t ls) {
+__device__ inline void lcd_event(Machine &m) {
     if (m.lcdc & 0x80) {
         uint32_t irq = stat_set_mode(m, m.next_mode);
         switch (m.stat_mode) {
         case 2:
             if (m.ly == 153) {
                 m.ly = 0;
-                m.cyc_adj += m.clock - m.clock % FRAME_CYCLES;
-                m.clock %= FRAME_CYCLES;
-                m.target %= FRAME_CYCLES;
+                if (m.target % FRAME_CYCLES == 0) {
+                    // frame-aligned LCD (the normal case): PyBoy's `clock %= 70224; target %= 70224` subtracts exactly
+                    // `target` from both, whenever this event is applied (lcd_catch_up may apply it late)
+                    m.cyc_adj += m.target;
+                    m.clock -= m.target;
+                    m.target = 0;
+                } else {  // unaligned (after an LCD-off period): applied at its own tick only, see lcd_deadline
+                    m.cyc_adj += m.clock - m.clock % FRAME_CYCLES;
+                    m.clock %= FRAME_CYCLES;
+                    m.target %= FRAME_CYCLES;
+                }
             } else {
                 m.ly = (m.ly + 1) & 0xFF;
             }
@@ -443,7 +456,7 @@ __device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uin
                     m.lp_dirty--;
                 }
                 if (!m.disable_renderer) {
-                    m.ly_window = render_line_out(m.memb, m.fb, m.lcdc, m.scroll, m.pal, m.ly_window, m.ly, line, keys, ls);
+                    m.ly_window = render_line_out(m.memb, m.fb, m.lcdc, m.scroll, m.pal, m.ly_window, m.ly, m.rline, m.rkeys, m.rls);
                     m.blank_shade = 0xFF;
                 }
             }
@@ -467,6 +480,82 @@ __device__ inline void lcd_event(Machine &m, uint32_t *line, uint32_t *keys, uin
         m.cyc_adj += m.clock - m.clock % FRAME_CYCLES;
         m.clock %= FRAME_CYCLES;
         lcd_blank_screen(m);
+    }
+}
+
+// ---- lazy LCD ------------------------------------------------------------------------------------------------
+// PyBoy's LCD.tick changes mode 442 times a frame, but while no STAT interrupt source is armed only two kinds of
+// mode change have effects outside the LCD's own registers: entering VBlank (IF bit 0, end of Motherboard.tick's frame)
+// and, on a frame whose renderer is enabled, the HBlank of a visible line (Renderer.scanline reads VRAM / OAM / the
+// scroll registers as they are at that moment).  Every other mode change ("soft") only rewrites LY, STAT's mode / LYC
+// bits, clock_target and the saved scanline parameters -- state nothing can see without a bus access.  So the interpreter
+// runs to the next HARD event (lcd_deadline) and the soft ones in between are applied, in order and with exactly the
+// effects LCD.tick would have had, by lcd_catch_up: at the deadline, and before any bus access that could observe or
+// change LCD state (every out-of-line read or write).  With a STAT source armed or TIMA running (a halted CPU then
+// ticks the timer once per LCD event) every event is hard and this degenerates to PyBoy's one-event-per-tick loop.
+
+// Cycles from lcd.clock to the next hard event; records in m.lazy whether soft events may be applied late.
+__device__ GB_NOINLINE int lcd_deadline(Machine &m) {
+    m.lazy = 0;
+    if (!(m.lcdc & 0x80)) return (int)(FRAME_CYCLES - m.clock);
+    const int t = (int)(m.target - m.clock);
+    // t <= 0: an event is already due (only inconsistent loaded states get here): strict one event per tick
+    if ((m.stat & 0x78) | (m.tmr & 0x04000000u) | (uint32_t)(t <= 0)) return t;
+#if defined(GB_NO_LAZY_LCD)
+    return t;
+#endif
+    const uint32_t nm = m.next_mode, ly = m.ly;
+    int d;
+    if (nm == 1) {
+        if (ly == 143) return t;           // the next event enters VBlank
+        if (ly - 144u > 8u) return t;      // inconsistent state: not lazy
+        // in VBlank: LY 153 -> 0 is `153 - ly` events away.  Its clock wrap can only be applied late when the frame is
+        // aligned (lcd_event); otherwise stop there.
+        const int wrap = t + 456 * (int)(153 - ly);
+        if ((m.target + 456u * (153 - ly)) % FRAME_CYCLES != 0) { m.lazy = 1; return wrap; }
+        d = m.disable_renderer ? wrap + 456 * 144 : wrap + 250;
+    } else if (nm == 2) {
+        if (ly == 153) {
+            if (m.target % FRAME_CYCLES != 0) return t;
+            d = m.disable_renderer ? t + 456 * 144 : t + 250;
+        } else {
+            if (ly > 142) return t;
+            d = m.disable_renderer ? t + 456 * (int)(143 - ly) : t + 250;
+        }
+    } else {
+        if (ly > 143) return t;
+        const int to_hblank = nm == 3 ? t + 170 : t;  // mode 2 -> 3 -> 0
+        d = m.disable_renderer ? to_hblank + 206 + 456 * (int)(143 - ly) : to_hblank;
+    }
+    m.lazy = 1;
+    return d;
+}
+
+// Applies every LCD event that is due (clock >= clock_target).  Not lazy: exactly one, as LCD.tick does per CPU tick.
+__device__ GB_NOINLINE void lcd_catch_up(Machine &m) {
+    if (!(m.lcdc & 0x80)) {
+        if (m.clock >= FRAME_CYCLES) lcd_event(m);
+        return;
+    }
+    const uint32_t lazy = m.lazy;
+    while ((int)(m.clock - m.target) >= 0) {
+        const uint32_t behind = m.clock - m.target;
+        if (lazy && m.disable_renderer && m.stat_mode == 0 && m.next_mode == 2 && m.ly < 142 && behind >= 456) {
+            // whole visible lines without rendering: mode 2 / 3 / 0 of each only move LY, STAT, clock_target and the saved
+            // scanline parameters -- closed form for k lines, staying below line 143 (whose HBlank arms the VBlank entry)
+            uint32_t k = behind / 456;
+            if (k > 142 - m.ly) k = 142 - m.ly;
+            for (uint32_t y = m.ly + 1; m.lp_dirty && y <= m.ly + k; y++) {
+                m.lp[y << 5] = make_uint2(m.scroll, m.lcdc);
+                m.lp_dirty--;
+            }
+            m.ly += k;
+            m.stat = (m.stat & 0xF8) | (m.lyc == m.ly ? 0x04 : 0);
+            m.target += 456 * k;
+            continue;
+        }
+        lcd_event(m);
+        if (!lazy) break;
     }
 }
 

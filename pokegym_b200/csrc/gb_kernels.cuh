@@ -27,13 +27,12 @@ struct RunParams {
     unsigned long long *counters;  // [0] instructions, [1] cycles, [2] frames, [3] faults
 };
 
-// Per-env slot in shared memory: the machine plus the four words the on-the-fly decoder returns its descriptor in.
+// Per-env slot in shared memory: the machine.
 // The slot stride is an odd number of 8-byte units, so the same field of 32 consecutive slots falls into 16 banks
 // (two-way conflicts, on cold paths only: the hot state is in registers).  The renderer's line buffer and sprite sort
 // keys follow as [word][slot] arrays (conflict-free).
 struct EnvSlot {
     Machine m;
-    uint32_t scratch[4];
 };
 #define ENV_SLOT_STRIDE ((sizeof(EnvSlot) + 7) / 8 * 8 + ((((sizeof(EnvSlot) + 7) / 8) & 1) ? 0 : 8))
 #define ENV_SMEM_BYTES(nslots) ((size_t)(nslots) * (ENV_SLOT_STRIDE + (FB_LINE_WORDS + 10) * 4))
@@ -42,12 +41,10 @@ struct EnvSlot {
 // around LCD events: cpu_run_to_event interprets until this env's LCD clock reaches its next mode change, then the
 // mode change is performed (scanline parameters, rendering, LY/STAT/interrupt flags).  All envs see the same number
 // of LCD events per frame, so a warp re-converges 442 times a frame and the scanline renderer runs with every lane.
-__device__ __forceinline__ void run_frames_env(EnvSlot &slot, const RunParams &p, int button, uint32_t *line, uint32_t *keys, uint32_t ls) {
-    Machine &m = slot.m;
+__device__ __forceinline__ void run_frames_env(Machine &m, const RunParams &p, int button) {
     RunCtx cx;
     cx.rom_dec = p.d.rom_dec;
     cx.bank_mask = p.bank_mask;
-    uint32_t bcde = m.bcde, hlaf = m.hlaf, sp = m.sp, pc = m.pc, rom_off = m.rom_off, n_instr = 0;
     for (int frame = 0; frame < p.n_frames; frame++) {
         // PyBoy.tick applies queued inputs before Motherboard.tick
         if (button >= 0) {
@@ -60,37 +57,19 @@ __device__ __forceinline__ void run_frames_env(EnvSlot &slot, const RunParams &p
         m.frame_done = 0;
         while (!done) {
             if (m.halted && !(m.iq | (m.iflag & m.ie & 0x1F) | (m.tmr & 0x04000000u)) && (m.lcdc & 0x80)) {
-                // Quiet HALT (nothing pending, TIMA stopped): CPU.tick is a no-op and Motherboard.tick jumps
-                // straight to the next LCD mode change, so the interpreter is not entered at all.
-                if (m.disable_renderer && m.stat_mode == 0 && m.next_mode == 2 && m.ly < 143 && !(m.stat & 0x78)) {
-                    // In HBlank with no STAT interrupt source armed and rendering off, the mode 2/3/0 events of
-                    // the remaining visible lines change only LY, STAT, the clocks and the saved scanline
-                    // parameters: run them in closed form up to HBlank of line 143 (the VBlank event that
-                    // follows raises the interrupt that ends the HALT).
-                    const uint32_t k = 143 - m.ly;
-                    for (uint32_t y = m.ly + 1; m.lp_dirty && y <= 143; y++) {
-                        m.lp[y << 5] = make_uint2(m.scroll, m.lcdc);
-                        m.lp_dirty--;
-                    }
-                    m.ly = 143;
-                    m.stat = (m.stat & 0xF8) | (m.lyc == 143 ? 0x04 : 0);
-                    m.next_mode = 1;
-                    m.target += 456 * k;
-                    const int adv = (int)(m.target - 206 - m.clock);  // clock of the last skipped mode change
-                    if (adv > 0) { m.divc += adv; m.clock += adv; }
-                }
-                const int a = (int)(m.target - m.clock);
+                // Quiet HALT (nothing pending, TIMA stopped): CPU.tick is a no-op and Motherboard.tick jumps from LCD mode
+                // change to mode change; only a hard one (VBlank entry, a rendered HBlank) can end the HALT or the frame,
+                // so jump there without entering the interpreter.
+                const int a = lcd_deadline(m);
                 if (a > 0) { m.divc += a; m.clock += a; }
             } else {
-                cpu_run_to_event(m, cx, bcde, hlaf, sp, pc, rom_off, n_instr, slot.scratch);
+                cpu_run_to_event(m, cx);
             }
-            lcd_event(m, line, keys, ls);
+            lcd_catch_up(m);
             done = m.frame_done;
             m.frame_done = 0;
         }
     }
-    m.bcde = bcde; m.hlaf = hlaf; m.sp = sp; m.pc = pc;
-    m.n_instr += n_instr;
 }
 
 // One thread per env; `lanes` envs per warp (the first `lanes` threads of each warp carry one; 32 = a full tile per
@@ -109,8 +88,9 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
     uint32_t *const line = (uint32_t *)((char *)s_env_slots + (size_t)nslots * ENV_SLOT_STRIDE) + si, *const keys = line + FB_LINE_WORDS * nslots;
     Machine &m = slot.m;
     machine_load(m, p.d, tile, lane);
+    m.rline = line; m.rkeys = keys; m.rls = nslots;
     const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
-    run_frames_env(slot, p, button, line, keys, nslots);
+    run_frames_env(m, p, button);
     machine_store(m, p.d, tile, lane);
     if (p.counters) {
         atomicAdd(&p.counters[0], (unsigned long long)m.n_instr);

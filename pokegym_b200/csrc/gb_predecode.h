@@ -12,7 +12,7 @@
 // bytes 0..7 of a PRMT source pair, so "which register" is a PRMT selector and the descriptor carries the selectors
 // ready-made:
 //
-//   x: handler | cycles << 8 | ex << 16 | op << 24
+//   x: handler | op << 8 | ex << 16 | cycles << 24
 //        cycles  T-cycles (condition false / unconditional)
 //        ex      low nibble: extra T-cycles when a conditional branch is taken; bits 4 / 7: flag value the
 //                condition expects (compared under the mask in `op`)
@@ -35,8 +35,7 @@
 #include <stdint.h>
 
 enum {
-    H_SLOW = 0,  // not pre-decodable here (instruction straddles a bank boundary): decode on the fly
-    H_MOV,       // rv = v : every 8-bit load / store and LD rr,nn (the selectors / PDF_WR say where it goes); NOP
+    H_MOV = 0,     // rv = v : every 8-bit load / store and LD rr,nn (the selectors / PDF_WR say where it goes); NOP
     H_HLI,       // rv = (pair + op) | v << 16 : LD A,(HL+-)  LD (HL+-),A  INC rr  DEC rr
     H_ARITH,     // ADD ADC SUB SBC CP on A with v   (op bit 0: carry in; ex = 0xFF for the subtractions)
     H_LOGIC,     // AND XOR OR on A with v           (ex = mask of a & v, op = mask of a ^ v)
@@ -50,7 +49,8 @@ enum {
     H_ROT,       // CB rotates / shifts / SWAP on v, and RLCA RRCA RLA RRA (op bit 3: Z forced clear)
     H_BIT,       // BIT b,v
     H_RESSET,    // RES / SET b,v
-    H_RARE,      // everything else, by opcode
+    H_RARE,      // everything else, by opcode (never executed by the fast loop)
+    H_SLOW,      // not pre-decodable here (instruction straddles a bank boundary): decoded on the fly by the slow tick
     H__COUNT
 };
 
@@ -63,9 +63,9 @@ enum {
 #define PDF_RETI 0x0400u  // RETI: IME = 1
 
 #define PD_H(x) ((x) & 0xFFu)
-#define PD_CYC(x) (((x) >> 8) & 0xFFu)
+#define PD_OP(x) (((x) >> 8) & 0xFFu)
 #define PD_EX(x) (((x) >> 16) & 0xFFu)
-#define PD_OP(x) ((x) >> 24)
+#define PD_CYC(x) ((x) >> 24)
 
 #if defined(__VECTOR_TYPES_H__)  // cuda_runtime.h (or the host-simulation shim) has defined uint4
 typedef uint4 pd_desc_t;
@@ -105,7 +105,7 @@ static inline void pd_b_write_pair(pd_builder *b, uint32_t p) {  // rv bytes 0,1
 }
 static inline pd_desc_t pd_b_done(const pd_builder *b) {
     pd_desc_t d;
-    d.x = b->h | (b->cyc << 8) | (b->ex << 16) | (b->op << 24);
+    d.x = b->h | (b->op << 8) | (b->ex << 16) | (b->cyc << 24);
     d.y = (b->imm & 0xFFFFu) | (b->len << 16) | (b->kind << 24);
     d.z = b->sel_lo | (b->sel_hi << 16);
     d.w = (b->srcsel & 0xFu) | (b->flags & 0xFFF0u) | (b->asel << 16);

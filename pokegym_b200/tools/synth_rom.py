@@ -1867,6 +1867,196 @@ def build_halt_edge_rom() -> bytes:
     return bytes(rom)
 
 
+def build_lcd_probe_rom(seed: int = 3, n_blocks: int = 400) -> bytes:
+    """A seeded random program of LCD *observations*: reads of LY / STAT / DIV, polling loops on LY and on the STAT mode,
+    writes to SCX/SCY/WX/WY/LYC/LY/STAT/LCDC/IE/TAC, LCD off-on periods, HALTs and OAM DMA, separated by delays of
+    random length so that every access lands at a different point of the scanline.  Everything read is folded into a
+    WRAM checksum and every handler folds LY and STAT at dispatch time, so an LCD mode change applied at the wrong
+    instruction boundary changes the state.  Exercises the lazy LCD of the CUDA interpreter (gb_device.cuh lcd_catch_up)
+    against the oracle's event-per-tick loop."""
+    rng = random.Random(seed)
+    rom = bytearray([0xFF]) * ROM_SIZE
+    a = Asm(rom)
+    for v in range(0, 0x40, 8):
+        a.org(v)
+        a.i("RET")
+    for v, name in ((0x40, "VBlank"), (0x48, "StatInt"), (0x50, "TimerInt"), (0x58, "SerialInt"), (0x60, "JoyInt")):
+        a.org(v)
+        a.i("JP nn", name)
+    a.org(0x100)
+    a.i("NOP")
+    a.i("JP nn", "Start")
+    a.org(0x150)
+
+    def fold():  # checksum = rlca(checksum + A), kept at 0xC100
+        a.i("PUSH HL")
+        a.i("LD HL,nn", 0xC100)
+        a.i("ADD A,(HL)")
+        a.i("RLCA")
+        a.i("LD (HL),A")
+        a.i("POP HL")
+
+    def handler(name: str, hram: int):
+        a.label(name)
+        a.i("PUSH AF")
+        a.i("LDH A,(n)", hram)
+        a.i("INC A")
+        a.i("LDH (n),A", hram)
+        a.i("LDH A,(n)", 0x44)
+        fold()
+        a.i("LDH A,(n)", 0x41)
+        fold()
+        a.i("POP AF")
+        a.i("RETI")
+
+    handler("VBlank", 0x90)
+    handler("StatInt", 0x91)
+    handler("TimerInt", 0x92)
+    handler("SerialInt", 0x94)
+    handler("JoyInt", 0x93)
+
+    def out(reg: int, v: int):
+        a.i("LD A,n", v)
+        a.i("LDH (n),A", reg)
+
+    a.label("Start")
+    a.i("DI")
+    a.i("LD SP,nn", 0xDFF0)
+    out(0x0F, 0)
+    out(0xFF, 0x01)
+    out(0x40, 0x91)
+    out(0x47, 0xE4)
+    out(0x48, 0xD0)
+    out(0x49, 0xE0)
+    out(0x00, 0x20)
+    a.i("LD HL,nn", 0x8000)
+    a.i("LD B,n", 0)
+    a.label("fill_tiles")
+    a.i("LD A,L")
+    a.i("XOR H")
+    a.i("RRCA")
+    a.i("LD (HL+),A")
+    a.i("DEC B")
+    a.i("JR NZ,e", "fill_tiles")
+    a.i("LD HL,nn", 0x9800)
+    a.i("LD BC,nn", 0x0800)
+    a.label("fill_map")
+    a.i("LD A,L")
+    a.i("AND n", 0x0F)
+    a.i("LD (HL+),A")
+    a.i("DEC BC")
+    a.i("LD A,B")
+    a.i("OR C")
+    a.i("JR NZ,e", "fill_map")
+    a.i("LD HL,nn", 0xFE00)
+    for v in (40, 30, 3, 0x00, 90, 100, 5, 0x30, 91, 20, 7, 0x60):
+        a.i("LD A,n", v)
+        a.i("LD (HL+),A")
+    a.i("EI")
+    a.label("MainLoop")
+    uid = [0]
+
+    def lab(prefix: str) -> str:
+        uid[0] += 1
+        return f"{prefix}{uid[0]}"
+
+    def delay():
+        n = rng.choice([1, 2, 3, 5, 9, 17, 33, 70, 150, 255])
+        l = lab("dly")
+        a.i("LD B,n", n)
+        a.label(l)
+        a.i("DEC B")
+        a.i("JR NZ,e", l)
+        if rng.random() < 0.3:
+            for _ in range(rng.randrange(1, 4)):
+                a.i("NOP")
+
+    lcd_on = True
+    for _ in range(n_blocks):
+        delay()
+        k = rng.randrange(20)
+        if k < 3:
+            a.i("LDH A,(n)", 0x44)
+            fold()
+        elif k < 6:
+            a.i("LDH A,(n)", 0x41)
+            fold()
+        elif k == 6:
+            a.i("LDH A,(n)", 0x04)
+            a.i("AND n", 0xF0)  # DIV's low bits depend on nothing else we check; keep the slow-moving part
+            fold()
+        elif k == 7:  # poll LY (bounded)
+            if lcd_on:
+                l, e = lab("ply"), lab("plx")
+                a.i("LD C,n", 200)
+                a.label(l)
+                a.i("LDH A,(n)", 0x44)
+                a.i("CP n", rng.randrange(0, 154))
+                a.i("JR Z,e", e)
+                a.i("DEC C")
+                a.i("JR NZ,e", l)
+                a.label(e)
+                a.i("LD A,C")
+                fold()
+        elif k == 8:  # poll the STAT mode (bounded)
+            l, e = lab("pst"), lab("psx")
+            a.i("LD C,n", 120)
+            a.label(l)
+            a.i("LDH A,(n)", 0x41)
+            a.i("AND n", 3)
+            a.i("CP n", rng.randrange(0, 4))
+            a.i("JR Z,e", e)
+            a.i("DEC C")
+            a.i("JR NZ,e", l)
+            a.label(e)
+            a.i("LD A,C")
+            fold()
+        elif k == 9:
+            a.i("LD A,(nn)", 0xC100)
+            a.i("LDH (n),A", rng.choice([0x42, 0x43, 0x4A, 0x4B]))
+        elif k == 10:
+            out(0x45, rng.choice([0, 1, 17, 80, 143, 144, 150, 153, 200]))
+        elif k == 11:
+            out(0x41, rng.choice([0x00, 0x00, 0x00, 0x08, 0x10, 0x20, 0x40, 0x48, 0x78]))
+        elif k == 12:
+            out(0xFF, rng.choice([0x01, 0x01, 0x03, 0x05, 0x11, 0x13, 0x07]))
+        elif k == 13:
+            if lcd_on and rng.random() < 0.4:
+                out(0x40, 0x11)
+                lcd_on = False
+            else:
+                out(0x40, rng.choice([0x91, 0xB1, 0xF3, 0xE3, 0x93, 0x97, 0x81]))
+                lcd_on = True
+        elif k == 14:
+            if not lcd_on:
+                out(0x40, 0x91)
+                lcd_on = True
+            a.i("HALT")
+        elif k == 15:
+            a.i("LDH A,(n)", 0x44)
+            a.i("ADD A,n", rng.choice([1, 3, 250]))
+            a.i("LDH (n),A", 0x44)
+        elif k == 16:
+            out(0x06, rng.choice([0x00, 0xF0, 0x80]))
+            out(0x07, rng.choice([0x00, 0x04, 0x05, 0x06, 0x07]))
+        elif k == 17:
+            out(0x46, 0xC1)
+        elif k == 18:
+            a.i(rng.choice(["DI", "EI"]))
+        else:
+            out(0x0F, rng.choice([0x00, 0x02, 0x04]))
+    if not lcd_on:
+        out(0x40, 0x91)
+    out(0x07, 0x00)
+    out(0xFF, 0x01)
+    out(0x41, 0x00)
+    a.i("EI")
+    a.i("JP nn", "MainLoop")
+    a.link()
+    finalize_header(rom, title="LCDPROBE")
+    return bytes(rom)
+
+
 def rom_catalog() -> Dict[str, Tuple]:
     return {
         "pokelike": (build_pokelike_rom, {}),
@@ -1875,4 +2065,6 @@ def rom_catalog() -> Dict[str, Tuple]:
         "conformance": (build_conformance_rom, {}),
         "conformance_b": (build_conformance_rom, {"seed": 99, "n_blocks": 900}),  # second instruction stream / interrupt phase
         "halt_edge": (build_halt_edge_rom, {}),
+        "lcd_probe": (build_lcd_probe_rom, {}),
+        "lcd_probe_b": (build_lcd_probe_rom, {"seed": 11, "n_blocks": 700}),
     }

@@ -6,6 +6,14 @@
 // save-state codec are exposed.
 #define GB_HOSTSIM 1
 #include "../../pokegym_b200/csrc/gb_hd.h"
+#include <stdio.h>
+#if defined(GB_TRACE)
+static FILE *g_trace = nullptr;
+static void gb_trace(uint32_t pc, uint32_t bcde, uint32_t hlaf, uint32_t sp, uint32_t dx) {
+    if (g_trace) fprintf(g_trace, "%04x %08x %08x %04x %08x\n", pc, bcde, hlaf, sp, dx);
+}
+extern "C" void hs_trace(const char *path) { if (g_trace) fclose(g_trace); g_trace = path ? fopen(path, "w") : nullptr; }
+#endif
 #include "../../pokegym_b200/csrc/gb_image.h"
 #include "../../pokegym_b200/csrc/gb_kernels.cuh"
 
@@ -87,7 +95,8 @@ int hs_run(void *p, const uint8_t *actions, int n_frames, int render_mode) {
         uint32_t line[FB_LINE_WORDS], keys[10];
         machine_load(slot.m, rp.d, env >> 5, env & 31);
         const int button = actions ? c_action_button[actions[env] & 7] : -1;
-        run_frames_env(slot, rp, button, line, keys, 1);
+        slot.m.rline = line; slot.m.rkeys = keys; slot.m.rls = 1;
+        run_frames_env(slot.m, rp, button);
         machine_store(slot.m, rp.d, env >> 5, env & 31);
         h->counters[0] += slot.m.n_instr; h->counters[1] += slot.m.n_cycles; h->counters[2] += n_frames;
     }

@@ -26,7 +26,7 @@ def _assert_same_states(gpu, cpu, envs, where):
         assert (xa.stat_mode, xa.ly_window, xa.fault) == (xb.stat_mode, xb.ly_window, xb.fault), where
 
 
-@pytest.mark.parametrize("rom_name,n,steps", [("pokelike", 72, 40), ("conformance", 40, 60), ("conformance_b", 40, 40), ("pokelike_timer", 33, 60), ("busy", 32, 30), ("halt_edge", 48, 120)])
+@pytest.mark.parametrize("rom_name,n,steps", [("pokelike", 72, 40), ("conformance", 40, 60), ("conformance_b", 40, 40), ("pokelike_timer", 33, 60), ("busy", 32, 30), ("halt_edge", 48, 120), ("lcd_probe", 40, 40), ("lcd_probe_b", 33, 40)])
 def test_run_action_matches_oracle(cuda_lib, oracle_lib, roms, rom_name, n, steps):
     import torch
 
