@@ -11,10 +11,12 @@
  *     across the ABI; gbenv_last_error() returns a static/handle-owned message.
  *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. PyTorch tensors);
  *     "host" pointers are ordinary host memory.  The library owns all emulator state.
- *   - a handle is bound to one CUDA device; calls are ordered on the `stream` argument
- *     (a cudaStream_t passed as void*; NULL = the legacy default stream, which is what PyTorch
- *     uses by default; the handle's internal stream is a blocking stream ordered with it) and asynchronous with
- *     respect to the host unless stated otherwise.  Not re-entrant per handle.
+ *   - a handle is bound to one CUDA device.  Entry points with a `stream` argument (a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream, which is what PyTorch uses by default) queue their
+ *     work on that stream; the others use the handle's own stream.  Whatever the streams, calls on one
+ *     handle take effect in CALL ORDER: when consecutive calls use different streams the later stream
+ *     waits for an event recorded on the earlier one.  Calls are asynchronous with respect to the host
+ *     unless stated otherwise.  Not re-entrant per handle.
  *   - there is NO CPU fallback: gbenv_create fails with GBENV_E_CUDA when no device is usable.
  *
  * The test oracle (oracle/liboracle.so) exports the same symbols with the prefix `oracle_`
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GBENV_ABI_VERSION 2 /* 2: info row widened from 64 to 72 doubles (per-item bag rewards) */
+#define GBENV_ABI_VERSION 3 /* 2: info row widened from 64 to 72 doubles; 3: gbenv_reset_dev, gbenv_submit_host / gbenv_fetch_host */
 
 #define GBENV_STATE_BYTES 142610 /* PyBoy v9 save-state length              */
 #define GBENV_OBS_H 72           /* environment.py:154-166: (144//2, 160//2, 4) uint8       */
@@ -101,6 +103,11 @@ int gbenv_screen(gbenv_t *h, int env, uint8_t *rgb_host);
  * only rows of reset envs are written.                                                          */
 int gbenv_reset(gbenv_t *h, const uint8_t *mask_host, int max_episode_steps, double reward_scale,
                 uint8_t *obs_dev, size_t obs_stride, void *stream);
+/* The same with a DEVICE mask (e.g. the `done` vector gbenv_step just wrote): nothing touches the host, so a vectoriser
+ * can auto-reset finished envs without a round trip.  Which envs still have their first reset -- the one that loads
+ * their save-state, environment.py:1241-1242 -- ahead of them is tracked on the device.                       */
+int gbenv_reset_dev(gbenv_t *h, const uint8_t *mask_dev, int max_episode_steps, double reward_scale,
+                    uint8_t *obs_dev, size_t obs_stride, void *stream);
 /* gbenv_step == Environment.step (environment.py:1336-1812) for every env:
  *   actions_dev uint8[n]; obs_dev uint8[n][obs_stride] (a slice of the rollout tensor);
  *   reward_dev double[n] (the reference returns Python floats); done_dev uint8[n]
@@ -113,6 +120,12 @@ int gbenv_step_host(gbenv_t *h, const uint8_t *actions_host, uint8_t *obs_host, 
                     uint8_t *done_host);
 int gbenv_reset_host(gbenv_t *h, const uint8_t *mask_host, int max_episode_steps, double reward_scale,
                      uint8_t *obs_host);
+/* Two-call form of gbenv_step_host: submit queues the step and returns at once, fetch blocks until the results of the
+ * OLDEST queued step are in the host buffers given to its submit.  Up to two steps may be in flight, so that the
+ * device-to-host copy of step t (23 KB per env) overlaps the emulation of step t+1.  Buffers should be pinned.   */
+int gbenv_submit_host(gbenv_t *h, const uint8_t *actions_host, uint8_t *obs_host, double *reward_host,
+                      uint8_t *done_host);
+int gbenv_fetch_host(gbenv_t *h);
 /* Episode-info scalars (environment.py:1621-1810 `stats` / `reward` numeric entries), one row of
  * GBENV_INFO_SCALARS doubles per env, written to info_dev[n][GBENV_INFO_SCALARS].               */
 int gbenv_get_info(gbenv_t *h, double *info_dev, void *stream);

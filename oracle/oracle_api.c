@@ -280,6 +280,17 @@ int oracle_step_host(oracle *h, const uint8_t *actions, uint8_t *obs, double *re
     return oracle_step(h, actions, obs, GBENV_OBS_BYTES, reward, done, NULL);
 }
 
+/* host memory is the oracle's only memory: the "device mask" form and the two-call step are the plain calls */
+int oracle_reset_dev(oracle *h, const uint8_t *mask, int max_episode_steps, double reward_scale, uint8_t *obs, size_t obs_stride, void *stream) {
+    return oracle_reset(h, mask, max_episode_steps, reward_scale, obs, obs_stride, stream);
+}
+
+int oracle_submit_host(oracle *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done) {
+    return oracle_step(h, actions, obs, GBENV_OBS_BYTES, reward, done, NULL);
+}
+
+int oracle_fetch_host(oracle *h) { return h ? GBENV_OK : GBENV_E_ARG; }
+
 int oracle_reset_host(oracle *h, const uint8_t *mask, int max_episode_steps, double reward_scale, uint8_t *obs) {
     return oracle_reset(h, mask, max_episode_steps, reward_scale, obs, GBENV_OBS_BYTES, NULL);
 }

@@ -18,7 +18,7 @@ STATE_BYTES = 142_610
 OBS_H, OBS_W, OBS_C = 72, 80, 4
 OBS_BYTES = OBS_H * OBS_W * OBS_C
 INFO_SCALARS = 72
-ABI_VERSION = 2
+ABI_VERSION = 3
 NUM_ACTIONS = 8
 ACT_FREQ = 24
 
@@ -75,6 +75,9 @@ _SIGS = {
     "write_mem": ([C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p], C.c_int),
     "screen": ([C.c_void_p, C.c_int, C.c_void_p], C.c_int),
     "reset": ([C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
+    "reset_dev": ([C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
+    "submit_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "fetch_host": ([C.c_void_p], C.c_int),
     "step": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "step_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "reset_host": ([C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p], C.c_int),
@@ -203,6 +206,19 @@ class Handle:
             self.lib.reset(self._h, _ptr(m), int(max_episode_steps), float(reward_scale), _ptr(obs), int(obs_stride), C.c_void_p(stream)),
             "reset",
         )
+
+    def reset_dev(self, obs, mask_dev=None, max_episode_steps: int = 20480, reward_scale: float = 4.0, obs_stride: int = OBS_BYTES, stream: int = 0):
+        """Environment.reset for the envs whose byte in the DEVICE mask is non-zero (None: all); nothing touches the host."""
+        self._check(
+            self.lib.reset_dev(self._h, _ptr(mask_dev), int(max_episode_steps), float(reward_scale), _ptr(obs), int(obs_stride), C.c_void_p(stream)),
+            "reset_dev",
+        )
+
+    def submit_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
+        self._check(self.lib.submit_host(self._h, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done)), "submit_host")
+
+    def fetch_host(self):
+        self._check(self.lib.fetch_host(self._h), "fetch_host")
 
     def step(self, actions, obs, reward, done, obs_stride: int = OBS_BYTES, stream: int = 0):
         self._check(self.lib.step(self._h, _ptr(actions), _ptr(obs), int(obs_stride), _ptr(reward), _ptr(done), C.c_void_p(stream)), "step")

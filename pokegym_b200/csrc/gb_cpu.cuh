@@ -120,12 +120,22 @@ struct CpuRegs {
 };
 
 // What the fast body may touch without leaving the loop.
-__device__ __forceinline__ bool fast_readable(uint32_t a) { return a < 0x8000u || a - 0xC000u < 0x3E00u || a - 0xFF80u < 0x7Fu; }
-// sound registers are dropped by PyBoy with sound disabled (pokegym's configuration): a store there is a no-op
-__device__ __forceinline__ bool fast_writable(uint32_t a) {
-    return a - 0xC000u < 0x3E00u || a - 0xFF80u < 0x7Fu || a - 0xFE00u < 0x100u || a - 0x8000u < 0x2000u || a - 0x2000u < 0x2000u || a - 0xFF10u < 0x30u;
+// Byte offset inside the env's interleaved plain-RAM array of a store the fast body may do itself, 0xFFFFFFFE for a store
+// that is dropped (sound registers: PyBoy with sound disabled, pokegym's configuration, ignores them), 0xFFFFFFFD for the
+// MBC3 ROM-bank register, or 0xFFFFFFFF when the store needs the full bus (IO, other MBC registers, cart RAM).
+#define FAST_WR_NONE 0xFFFFFFFFu
+#define FAST_WR_DROP 0xFFFFFFFEu
+#define FAST_WR_BANK 0xFFFFFFFDu
+__device__ __forceinline__ uint32_t mem_offset(uint32_t i) { return ((i >> 2) << 7) | (i & 3); }
+__device__ __forceinline__ uint32_t fast_store_target(uint32_t a) {
+    if (a - 0xC000u < 0x3E00u) return mem_offset(MEM_WRAM + (a & 0x1FFF));                               // WRAM and its echo
+    if (a - 0xFF80u < 0x7Fu || a - 0xFE00u < 0x100u) return mem_offset(MEM_HI + (a - 0xFE00));             // HRAM, OAM
+    if (a - 0x8000u < 0x2000u) return mem_offset(MEM_VRAM + (a - 0x8000));                                // VRAM
+    if (a - 0x2000u < 0x2000u) return FAST_WR_BANK;
+    if (a - 0xFF10u < 0x30u) return FAST_WR_DROP;
+    return FAST_WR_NONE;
 }
-// both bytes of a push below `sp` / a pop at `sp` inside work RAM (or its echo)
+// both bytes of a push below `sp` inside work RAM (or its echo)
 __device__ __forceinline__ bool fast_stack_push(uint32_t sp) { return sp - 0xC002u < 0x3DFFu; }
 
 // One instruction, given its control word.  FAST: returns false -- having changed nothing -- when the instruction needs
@@ -135,11 +145,14 @@ template <bool FAST>
 __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &mode, uint32_t &cyc, uint8_t *memb,
                                          const uint8_t *rom, uint32_t bank_mask) {
     uint32_t bcde = r.bcde, hlaf = r.hlaf, sp = r.sp;
-    auto rd8 = [&](uint32_t a) -> uint32_t {  // Motherboard.getitem
+    bool declined = false;
+    auto rd8 = [&](uint32_t a) -> uint32_t {  // Motherboard.getitem; FAST: WRAM (+ echo), ROM and HRAM, else decline
         if (FAST) {
-            if (a < 0x8000) return __ldg(rom + (a + (a >> 14) * rom_off));
-            const uint32_t i = a >= 0xFE00u ? MEM_HI + (a - 0xFE00) : MEM_WRAM + (a & 0x1FFF);
-            return memb[((i >> 2) << 7) | (i & 3)];
+            if (a - 0xC000u < 0x3E00u) return memb[mem_offset(MEM_WRAM + (a & 0x1FFF))];
+            if (a < 0x8000u) return __ldg(rom + (a + (a >> 14) * rom_off));
+            if (a - 0xFF80u < 0x7Fu) return memb[mem_offset(MEM_HI + (a - 0xFE00))];
+            declined = true;
+            return 0;
         }
         return bus_read_full(m, a);
     };
@@ -147,18 +160,19 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     const uint32_t w = d.w, h = d.x & 0xFF;
     uint32_t v = gb_prmt(bcde, hlaf, w);  // byte 0 = source register (upper bytes: don't care)
     if (w & PDF_IMM) v = d.y & 0xFFFFu;
-    uint32_t wa = 0;
+    uint32_t wa = 0, wt = 0;  // store address; FAST: its classified target
     if (FAST && h >= H_RARE) return false;  // rare opcodes, on-the-fly decode
     if (w & (PDF_RD | PDF_WR)) {
         wa = (w & PDF_AIMM) ? (d.y & 0xFFFFu) : (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu);
         if (w & PDF_ASP) wa = sp;
-        if (FAST) {
-            if ((w & PDF_WR) && !fast_writable(wa)) return false;
-            if ((w & PDF_RD) && !(fast_readable(wa) && (!(w & PDF_RD16) || fast_readable((wa + 1) & 0xFFFF)))) return false;
+        if (FAST && (w & PDF_WR)) {
+            wt = fast_store_target(wa);
+            if (wt == FAST_WR_NONE) return false;
         }
         if (w & PDF_RD) {
             v = rd8(wa);
             if (w & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
+            if (FAST && declined) return false;
         }
     }
     // ---- handler
@@ -167,9 +181,9 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     cyc = d.x >> 24;
 #define PAIR_OPERAND() (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu)
     // The most frequent handlers are tested first, one compare each; the rest share a switch.
-    if (h == H_MOV) {
+    if (w & PDF_MOV) {
         // plain moves (a third of all instructions) are done: rv = v
-    } else if (h == H_JUMP) {
+    } else if (w & PDF_JUMP) {
         if (((f ^ ex) & op) == 0) { next_pc = imm16; cyc += ex & 0xF; }
     } else if (h == H_INCDEC) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
         const uint32_t b = v & 0xFF, sum = b + op, res = sum & 0xFF;
@@ -314,24 +328,23 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     // ---- bus writes.  wn = PDF_WR: byte wv at wa; 2: low byte of wv at wa, then high byte at wa - 1 (pushes); 3: low byte
     // at wa, then high byte at wa + 1 (LD (nn),SP)
     if (wn) {
-        const uint32_t count = (wn & 3) ? 2u : 1u, second = (wn == 2 ? wa - 1 : wa + 1) & 0xFFFF;
-#pragma unroll 1
-        for (uint32_t i = 0; i < count; i++) {
-            const uint32_t a = i ? second : wa, b = (i ? wv >> 8 : wv) & 0xFF;
-            if (FAST) {
-                if (a - 0x2000u < 0x2000u) {  // MBC3 ROM bank select (constant traffic in banked games)
-                    uint32_t bank = b & 0x7F;
-                    bank = bank ? bank : 1;
-                    m.rombank = bank;
-                    rom_off = (bank_mask ? (bank & bank_mask) : (bank % m.rom_banks)) * 0x4000u - 0x4000u;
-                    m.rom_off = rom_off;
-                } else if (a - 0xFF10u >= 0x30u) {  // (sound registers: dropped)
-                    const uint32_t k = a >= 0xFE00u ? MEM_HI + (a - 0xFE00) : a >= 0xC000u ? MEM_WRAM + (a & 0x1FFF) : MEM_VRAM + (a - 0x8000);
-                    memb[((k >> 2) << 7) | (k & 3)] = (uint8_t)b;
-                }
-            } else {
-                bus_write_full(m, a, b);
+        if (FAST) {
+            if (wn == 2) {  // push: both bytes in work RAM (checked by the handler); an odd address keeps them in one word
+                const uint32_t k1 = mem_offset(MEM_WRAM + (wa & 0x1FFF)), k2 = mem_offset(MEM_WRAM + ((wa - 1) & 0x1FFF));
+                memb[k1] = (uint8_t)wv;
+                memb[k2] = (uint8_t)(wv >> 8);
+            } else if (wt < FAST_WR_BANK) {
+                memb[wt] = (uint8_t)wv;
+            } else if (wt == FAST_WR_BANK) {  // MBC3 ROM bank select (constant traffic in banked games)
+                uint32_t bank = wv & 0x7F;
+                bank = bank ? bank : 1;
+                m.rombank = bank;
+                rom_off = (bank_mask ? (bank & bank_mask) : (bank % m.rom_banks)) * 0x4000u - 0x4000u;
+                m.rom_off = rom_off;
             }
+        } else {
+            const uint32_t count = (wn & 3) ? 2u : 1u, second = (wn == 2 ? wa - 1 : wa + 1) & 0xFFFF;
+            for (uint32_t i = 0; i < count; i++) bus_write_full(m, i ? second : wa, (i ? wv >> 8 : wv) & 0xFF);
         }
     }
     return true;

@@ -25,8 +25,12 @@ struct gbenv {
     WrapArrays w{};
     cudaStream_t stream = nullptr;
     std::vector<StateTemplate> templates;
-    std::vector<int> initial_template;  // per env, -1 = none
-    std::vector<int> reset_count;       // host mirror of WrapState.reset_count
+    std::vector<int> initial_template;  // per env, -1 = none (host copy; the device copy d_init_tmpl is what resets read)
+    int32_t *d_init_tmpl = nullptr;     // [n]
+    uint32_t **d_tmpl_images = nullptr; // [MAX_TEMPLATES] device pointers of the template images
+    int32_t *d_tmpl_versions = nullptr; // [MAX_TEMPLATES]
+    bool tmpl_dirty = false;            // host-side template tables changed since the last upload
+    bool loads_pending = false;         // some env may still have its first reset (which loads its save-state) ahead
     unsigned long long *d_counters = nullptr;
     uint32_t *d_stage_image = nullptr;
     uint8_t *d_stage_buf = nullptr;  // 64 KiB scratch for bus access
@@ -34,8 +38,16 @@ struct gbenv {
     int32_t *d_env_ids = nullptr;
     uint8_t *d_mask = nullptr;
     // staging for the *_host entry points
-    uint8_t *d_actions = nullptr, *d_obs = nullptr, *d_done = nullptr;
-    double *d_reward = nullptr;
+    // two slots: step t+1 is emulated while the results of step t travel to the host (gbenv_submit_host / gbenv_fetch_host)
+    uint8_t *d_actions[2] = {nullptr, nullptr}, *d_obs[2] = {nullptr, nullptr}, *d_done[2] = {nullptr, nullptr};
+    double *d_reward[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_stepped[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    unsigned long long submitted = 0, fetched = 0;
+    // cross-stream ordering of the calls on this handle (use_stream)
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t ev_order = nullptr;
     // CUDA-event ring: slot k holds {start, after k_run_frames, after k_wrap_*} of step k (mod EV_RING)
     static const int EV_RING = 64;
     cudaEvent_t ev[EV_RING][3] = {};
@@ -48,7 +60,8 @@ struct gbenv {
     std::string err;
 };
 
-static std::string g_err;
+static thread_local std::string g_err;
+static const int MAX_TEMPLATES = 1024;
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -66,10 +79,21 @@ static int fail(gbenv *h, int code, const char *msg) {
     return code;
 }
 
-// NULL means the legacy default stream -- the stream PyTorch uses unless told otherwise -- so a caller that
-// passes nothing is ordered after its own tensor copies.  The handle's private stream is a blocking stream,
-// i.e. implicitly ordered with the legacy default stream in both directions.
-static cudaStream_t pick(gbenv *h, void *stream) { (void)h; return (cudaStream_t)stream; }
+// Every entry point does its work on ONE stream: the caller's (`stream` argument; NULL = the legacy default stream, which
+// is what PyTorch uses unless told otherwise) or the handle's own.  Calls on one handle take effect in call order whatever
+// streams they use: when the stream changes, the new one first waits for an event recorded on the previous one, so e.g.
+// gbenv_save_state (own stream) after gbenv_step on a PyTorch side stream sees the stepped state.
+static cudaStream_t use_stream(gbenv *h, cudaStream_t s) {
+    if (h->last_stream_valid && s != h->last_stream && h->ev_order) {
+        cudaEventRecord(h->ev_order, h->last_stream);
+        cudaStreamWaitEvent(s, h->ev_order, 0);
+    }
+    h->last_stream = s;
+    h->last_stream_valid = true;
+    return s;
+}
+static cudaStream_t pick(gbenv *h, void *stream) { return use_stream(h, (cudaStream_t)stream); }
+static cudaStream_t own(gbenv *h) { return use_stream(h, h->stream); }
 
 // ------------------------------------------------------------------------------- lifetime
 
@@ -101,12 +125,19 @@ static int scatter(gbenv *h, const uint32_t *d_image, int version, const int32_t
 extern "C" int gbenv_destroy(gbenv *h) {
     if (!h) return GBENV_E_ARG;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
     for (auto &t : h->templates) cudaFree(t.d_image);
     cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree((void *)h->d.rom); cudaFree((void *)h->d.rom_dec);
     cudaFree(h->w.state); cudaFree(h->w.visited); cudaFree(h->w.counts_map); cudaFree(h->w.cm_hash);
     cudaFree(h->d_counters); cudaFree(h->d_stage_image); cudaFree(h->d_stage_buf); cudaFree(h->d_info_rows);
-    cudaFree(h->d_env_ids); cudaFree(h->d_mask); cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_reward);
+    cudaFree(h->d_env_ids); cudaFree(h->d_mask); cudaFree(h->d_init_tmpl); cudaFree(h->d_tmpl_images); cudaFree(h->d_tmpl_versions);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(h->d_actions[k]); cudaFree(h->d_obs[k]); cudaFree(h->d_done[k]); cudaFree(h->d_reward[k]);
+        if (h->ev_stepped[k]) cudaEventDestroy(h->ev_stepped[k]);
+        if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
+    }
+    if (h->ev_order) cudaEventDestroy(h->ev_order);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto &slot : h->ev)
         for (auto &e : slot)
             if (e) cudaEventDestroy(e);
@@ -115,9 +146,25 @@ extern "C" int gbenv_destroy(gbenv *h) {
     return GBENV_OK;
 }
 
+static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t rom_len, int device_id);
+
 extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len, int device_id, gbenv **out) {
+    if (!out) return fail(nullptr, GBENV_E_ARG, "gbenv_create: bad argument");
     gbenv *h = nullptr;
-    if (n_envs <= 0 || !rom_host || rom_len < 0x8000 || (rom_len & 0x3FFF) || !out) return fail(nullptr, GBENV_E_ARG, "gbenv_create: bad argument");
+    int rc = create_impl(h, n_envs, rom_host, rom_len, device_id);
+    if (rc != GBENV_OK) {  // nothing is leaked on a failed create: the message moves to the global slot, the handle goes
+        if (h) {
+            if (!h->err.empty()) g_err = h->err;
+            gbenv_destroy(h);
+        }
+        return rc;
+    }
+    *out = h;
+    return GBENV_OK;
+}
+
+static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t rom_len, int device_id) {
+    if (n_envs <= 0 || !rom_host || rom_len < 0x8000 || (rom_len & 0x3FFF)) return fail(nullptr, GBENV_E_ARG, "gbenv_create: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, GBENV_E_CUDA, "gbenv_create: no CUDA device (this library has no CPU fallback)");
@@ -128,12 +175,10 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     h->n_tiles = (n_envs + GB_TILE - 1) / GB_TILE;
     h->device = device_id;
     h->initial_template.assign(n_envs, -1);
-    h->reset_count.assign(n_envs, 0);
 #define ALLOC(ptr, bytes)                                              \
     do {                                                               \
         if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) {     \
-            g_err = "gbenv_create: cudaMalloc failed for " #ptr;       \
-            gbenv_destroy(h);                                          \
+            h->err = "gbenv_create: cudaMalloc failed for " #ptr;      \
             return GBENV_E_NOMEM;                                      \
         }                                                              \
         cudaMemset((ptr), 0, (bytes));                                 \
@@ -206,8 +251,18 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     ALLOC(h->d_info_rows, (size_t)n_envs * GBENV_INFO_SCALARS * sizeof(double));
     ALLOC(h->d_env_ids, (size_t)n_envs * sizeof(int32_t));
     ALLOC(h->d_mask, (size_t)n_envs);
+    ALLOC(h->d_init_tmpl, (size_t)n_envs * sizeof(int32_t));
+    ALLOC(h->d_tmpl_images, MAX_TEMPLATES * sizeof(uint32_t *));
+    ALLOC(h->d_tmpl_versions, MAX_TEMPLATES * sizeof(int32_t));
 #undef ALLOC
+    CK(cudaMemset(h->d_init_tmpl, 0xFF, (size_t)n_envs * sizeof(int32_t)));  // -1: no save-state to load
     CK(cudaStreamCreate(&h->stream));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&h->ev_stepped[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
+    }
     for (auto &slot : h->ev)
         for (auto &e : slot) CK(cudaEventCreate(&e));
     CK(cudaMemcpy(d_rom, rom_host, rom_len, cudaMemcpyHostToDevice));
@@ -224,9 +279,8 @@ extern "C" int gbenv_create(int n_envs, const uint8_t *rom_host, size_t rom_len,
     power_on_image(img);
     CK(cudaMemcpyAsync(h->d_stage_image, img.data(), IMG_WORDS * 4, cudaMemcpyHostToDevice, h->stream));
     int rc = scatter(h, h->d_stage_image, 0 /* raw image, no load_state merge */, nullptr, 0, h->stream);
-    if (rc) { g_err = h->err; gbenv_destroy(h); return rc; }
+    if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    *out = h;
     return GBENV_OK;
 }
 
@@ -239,6 +293,7 @@ extern "C" int gbenv_set_lanes_per_warp(gbenv *h, int lanes) {
 extern "C" int gbenv_sync(gbenv *h) {
     if (!h) return GBENV_E_ARG;
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     CK(cudaStreamSynchronize(h->stream));
     return GBENV_OK;
 }
@@ -253,10 +308,12 @@ extern "C" int gbenv_add_state_template(gbenv *h, const uint8_t *blob, size_t le
     std::string err;
     int rc = blob_to_image(blob, len, img, &ver, err);
     if (rc) return fail(h, rc, err.c_str());
+    if ((int)h->templates.size() >= MAX_TEMPLATES) return fail(h, GBENV_E_ARG, "gbenv_add_state_template: too many templates");
     StateTemplate t{nullptr, ver};
     CK(cudaMalloc((void **)&t.d_image, IMG_WORDS * sizeof(uint32_t)));
     CK(cudaMemcpy(t.d_image, img.data(), IMG_WORDS * sizeof(uint32_t), cudaMemcpyHostToDevice));
     h->templates.push_back(t);
+    h->tmpl_dirty = true;
     *id_out = (int)h->templates.size() - 1;
     return GBENV_OK;
 }
@@ -264,6 +321,7 @@ extern "C" int gbenv_add_state_template(gbenv *h, const uint8_t *blob, size_t le
 extern "C" int gbenv_load_template(gbenv *h, const int32_t *env_ids, int n, int tid) {
     if (!h || tid < 0 || tid >= (int)h->templates.size()) return fail(h, GBENV_E_ARG, "gbenv_load_template: bad template id");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     return scatter(h, h->templates[tid].d_image, h->templates[tid].version, env_ids, n, h->stream);
 }
 
@@ -277,12 +335,15 @@ extern "C" int gbenv_set_initial_template(gbenv *h, const int32_t *env_ids, int 
     } else {
         for (auto &t : h->initial_template) t = tid;
     }
+    h->tmpl_dirty = true;
+    h->loads_pending = true;
     return GBENV_OK;
 }
 
 extern "C" int gbenv_power_on(gbenv *h, const int32_t *env_ids, int n) {
     if (!h) return GBENV_E_ARG;
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     // a power-on is a complete re-initialisation: unlike a state load it also resets STAT mode / ly_window
     std::vector<uint32_t> img;
     power_on_image(img);
@@ -294,6 +355,7 @@ extern "C" int gbenv_power_on(gbenv *h, const int32_t *env_ids, int n) {
 extern "C" int gbenv_save_state(gbenv *h, int env, uint8_t *blob) {
     if (!h || env < 0 || env >= h->n || !blob) return fail(h, GBENV_E_ARG, "gbenv_save_state: bad argument");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     k_gather_image<<<(IMG_WORDS + 255) / 256, 256, 0, h->stream>>>(h->d, h->d_stage_image, env);
     h->launches++;
     CK(cudaGetLastError());
@@ -353,6 +415,7 @@ extern "C" int gbenv_send_input(gbenv *h, int button, int pressed, void *stream)
 static int bus_access(gbenv *h, int env, uint32_t addr, uint32_t n, uint8_t *host, int write) {
     if (!h || env < 0 || env >= h->n || !host || addr + n > 0x10000 || n == 0) return fail(h, GBENV_E_ARG, "bus access: bad argument");
     CK(cudaSetDevice(h->device));
+    own(h);
     if (write) CK(cudaMemcpyAsync(h->d_stage_buf, host, n, cudaMemcpyHostToDevice, h->stream));
     k_bus_access<<<1, 1, 0, h->stream>>>(h->d, env, addr, n, h->d_stage_buf, write);
     h->launches++;
@@ -370,6 +433,7 @@ extern "C" int gbenv_write_mem(gbenv *h, int env, uint32_t addr, uint32_t n, con
 extern "C" int gbenv_screen(gbenv *h, int env, uint8_t *rgb) {
     if (!h || env < 0 || env >= h->n || !rgb) return fail(h, GBENV_E_ARG, "gbenv_screen: bad argument");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     k_gather_image<<<(IMG_WORDS + 255) / 256, 256, 0, h->stream>>>(h->d, h->d_stage_image, env);
     h->launches++;
     CK(cudaGetLastError());
@@ -386,39 +450,74 @@ extern "C" int gbenv_screen(gbenv *h, int env, uint8_t *rgb) {
 
 // ------------------------------------------------------------------------------- Environment API
 
-extern "C" int gbenv_reset(gbenv *h, const uint8_t *mask_host, int max_episode_steps, double reward_scale, uint8_t *obs_dev, size_t obs_stride,
-                           void *stream) {
+// environment.py:1241-1242: the save-state is loaded on an env's FIRST reset only.  Which envs that concerns is decided on
+// the device (WrapState.reset_count == 0 and a template assigned), so a reset never needs the host to look at per-env data.
+// grid: (ceil(n / 32), ceil(IMG_WORDS / 8)); block (32, 8) as k_scatter_image
+__global__ void k_reset_load(DevArrays d, const WrapState *st, const int32_t *init_tmpl, uint32_t *const *tmpl_images, const int32_t *tmpl_versions,
+                             const uint8_t *mask, int n) {
+    int env = blockIdx.x * 32 + threadIdx.x;
+    uint32_t j = blockIdx.y * 8 + threadIdx.y;
+    if (env >= n || j >= IMG_WORDS || (mask && !mask[env])) return;
+    int tid = init_tmpl[env];
+    if (tid < 0 || st[env].reset_count != 0) return;
+    const uint32_t *image = tmpl_images[tid];
+    uint32_t v = image[j];
+    uint32_t *slot = image_slot(d, env, j);
+    if (j >= IMG_REGS) v = merge_loaded_reg(j - IMG_REGS, *slot, v, tmpl_versions[tid], image[IMG_REGS + R_LCD0] & 0xFF);
+    *slot = v;
+}
+
+static int upload_template_tables(gbenv *h, cudaStream_t st) {
+    if (!h->tmpl_dirty) return GBENV_OK;
+    std::vector<uint32_t *> ptrs(h->templates.size());
+    std::vector<int32_t> vers(h->templates.size());
+    for (size_t i = 0; i < h->templates.size(); i++) { ptrs[i] = h->templates[i].d_image; vers[i] = h->templates[i].version; }
+    std::vector<int32_t> init(h->initial_template.begin(), h->initial_template.end());
+    // pageable host vectors: these copies return after the data has been staged, so the vectors may go out of scope
+    if (!ptrs.empty()) {
+        CK(cudaMemcpyAsync(h->d_tmpl_images, ptrs.data(), ptrs.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_tmpl_versions, vers.data(), vers.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(h->d_init_tmpl, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    h->tmpl_dirty = false;
+    return GBENV_OK;
+}
+
+// Environment.reset for the envs with mask_dev[e] != 0 (mask_dev == NULL: all), everything on the device, asynchronous.
+extern "C" int gbenv_reset_dev(gbenv *h, const uint8_t *mask_dev, int max_episode_steps, double reward_scale, uint8_t *obs_dev, size_t obs_stride,
+                               void *stream) {
     if (!h || !obs_dev || obs_stride < GBENV_OBS_BYTES || (obs_stride & 3)) return fail(h, GBENV_E_ARG, "gbenv_reset: bad argument");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = pick(h, stream);
-    const uint8_t *d_mask = nullptr;
-    if (mask_host) {
-        CK(cudaMemcpyAsync(h->d_mask, mask_host, h->n, cudaMemcpyHostToDevice, st));
-        d_mask = h->d_mask;
-    }
+    int rc = upload_template_tables(h, st);
+    if (rc) return rc;
     int blocks = (h->n + 127) / 128;
-    k_wrap_reset_pre<<<blocks, 128, 0, st>>>(h->d, h->w, d_mask);  // environment.py:1239: D778 |= 0x10 before the load
+    k_wrap_reset_pre<<<blocks, 128, 0, st>>>(h->d, h->w, mask_dev);  // environment.py:1239: D778 |= 0x10 before the load
     h->launches++;
-    CK(cudaGetLastError());
-    // environment.py:1241-1242: the save-state is loaded on an env's first reset only
-    std::vector<std::vector<int32_t>> by_template(h->templates.size());
-    for (int e = 0; e < h->n; e++) {
-        if (mask_host && !mask_host[e]) continue;
-        if (h->reset_count[e] == 0 && h->initial_template[e] >= 0) by_template[h->initial_template[e]].push_back(e);
-        h->reset_count[e]++;
+    if (h->loads_pending) {
+        dim3 block(32, 8), grid((h->n + 31) / 32, (IMG_WORDS + 7) / 8);
+        k_reset_load<<<grid, block, 0, st>>>(h->d, h->w.state, h->d_init_tmpl, h->d_tmpl_images, h->d_tmpl_versions, mask_dev, h->n);
+        h->launches++;
+        if (!mask_dev) h->loads_pending = false;  // every env has had its first reset now
     }
-    for (size_t t = 0; t < by_template.size(); t++) {
-        auto &ids = by_template[t];
-        if (ids.empty()) continue;
-        bool all = (int)ids.size() == h->n;
-        int rc = scatter(h, h->templates[t].d_image, h->templates[t].version, all ? nullptr : ids.data(), (int)ids.size(), st);
-        if (rc) return rc;
-    }
-    k_wrap_reset_post<<<blocks, 128, 0, st>>>(h->d, h->w, d_mask, max_episode_steps, reward_scale);
-    k_wrap_obs<<<h->n_tiles, 256, 0, st>>>(h->d, h->w, d_mask, obs_dev, obs_stride);
+    k_wrap_reset_post<<<blocks, 128, 0, st>>>(h->d, h->w, mask_dev, max_episode_steps, reward_scale);
+    k_wrap_obs<<<h->n_tiles, 256, 0, st>>>(h->d, h->w, mask_dev, obs_dev, obs_stride);
     h->launches += 2;
     CK(cudaGetLastError());
-    if (mask_host) CK(cudaStreamSynchronize(st));  // d_mask is reused
+    return GBENV_OK;
+}
+
+extern "C" int gbenv_reset(gbenv *h, const uint8_t *mask_host, int max_episode_steps, double reward_scale, uint8_t *obs_dev, size_t obs_stride,
+                           void *stream) {
+    if (!h) return GBENV_E_ARG;
+    if (!mask_host) return gbenv_reset_dev(h, nullptr, max_episode_steps, reward_scale, obs_dev, obs_stride, stream);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = pick(h, stream);
+    CK(cudaMemcpyAsync(h->d_mask, mask_host, h->n, cudaMemcpyHostToDevice, st));
+    int rc = gbenv_reset_dev(h, h->d_mask, max_episode_steps, reward_scale, obs_dev, obs_stride, stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));  // d_mask is reused by the next call
     return GBENV_OK;
 }
 
@@ -464,27 +563,61 @@ extern "C" int gbenv_step(gbenv *h, const uint8_t *actions_dev, uint8_t *obs_dev
 }
 
 static int ensure_host_staging(gbenv *h) {
-    if (h->d_actions) return GBENV_OK;
-    CK(cudaMalloc((void **)&h->d_actions, h->n));
-    CK(cudaMalloc((void **)&h->d_obs, (size_t)h->n * GBENV_OBS_BYTES));
-    CK(cudaMalloc((void **)&h->d_done, h->n));
-    CK(cudaMalloc((void **)&h->d_reward, (size_t)h->n * sizeof(double)));
+    if (h->d_actions[0]) return GBENV_OK;
+    for (int k = 0; k < 2; k++) {
+        CK(cudaMalloc((void **)&h->d_actions[k], h->n));
+        CK(cudaMalloc((void **)&h->d_obs[k], (size_t)h->n * GBENV_OBS_BYTES));
+        CK(cudaMalloc((void **)&h->d_done[k], h->n));
+        CK(cudaMalloc((void **)&h->d_reward[k], (size_t)h->n * sizeof(double)));
+    }
     return GBENV_OK;
 }
 
-extern "C" int gbenv_step_host(gbenv *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done) {
-    if (!h || !actions || !obs || !reward || !done) return fail(h, GBENV_E_ARG, "gbenv_step_host: bad argument");
+// Queues one Environment.step with HOST buffers and returns at once: actions H2D, the three kernels, then -- on a second
+// stream -- obs / reward / done D2H into the caller's buffers.  gbenv_fetch_host blocks until the OLDEST queued step has
+// landed.  At most two steps may be in flight (two device staging slots), which is what lets the 23 KB-per-env observation
+// copy of step t overlap the emulation of step t+1.
+extern "C" int gbenv_submit_host(gbenv *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done) {
+    if (!h || !actions || !obs || !reward || !done) return fail(h, GBENV_E_ARG, "gbenv_submit_host: bad argument");
+    if (h->submitted - h->fetched >= 2) return fail(h, GBENV_E_ARG, "gbenv_submit_host: two steps already in flight, fetch one first");
     CK(cudaSetDevice(h->device));
     int rc = ensure_host_staging(h);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_actions, actions, h->n, cudaMemcpyHostToDevice, h->stream));
-    rc = gbenv_step(h, h->d_actions, h->d_obs, GBENV_OBS_BYTES, h->d_reward, h->d_done, h->stream);
+    const int k = (int)(h->submitted & 1);
+    cudaStream_t st = own(h);
+    CK(cudaStreamWaitEvent(st, h->ev_copied[k], 0));  // slot k's previous results have left the device
+    CK(cudaMemcpyAsync(h->d_actions[k], actions, h->n, cudaMemcpyHostToDevice, st));
+    rc = gbenv_step(h, h->d_actions[k], h->d_obs[k], GBENV_OBS_BYTES, h->d_reward[k], h->d_done[k], st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(obs, h->d_obs, (size_t)h->n * GBENV_OBS_BYTES, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(reward, h->d_reward, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(done, h->d_done, h->n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(h->ev_stepped[k], st));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_stepped[k], 0));
+    CK(cudaMemcpyAsync(obs, h->d_obs[k], (size_t)h->n * GBENV_OBS_BYTES, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaMemcpyAsync(reward, h->d_reward[k], (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaMemcpyAsync(done, h->d_done[k], h->n, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(h->ev_copied[k], h->copy_stream));
+    h->submitted++;
     return GBENV_OK;
+}
+
+extern "C" int gbenv_fetch_host(gbenv *h) {
+    if (!h) return GBENV_E_ARG;
+    if (h->fetched == h->submitted) return fail(h, GBENV_E_ARG, "gbenv_fetch_host: nothing in flight");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev_copied[h->fetched & 1]));
+    h->fetched++;
+    return GBENV_OK;
+}
+
+// Same call, synchronous: copies in, steps, copies out.  This is the entry point a pokegym worker would call.
+extern "C" int gbenv_step_host(gbenv *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done) {
+    if (!h) return GBENV_E_ARG;
+    while (h->fetched < h->submitted) {
+        int rc = gbenv_fetch_host(h);
+        if (rc) return rc;
+    }
+    int rc = gbenv_submit_host(h, actions, obs, reward, done);
+    if (rc) return rc;
+    return gbenv_fetch_host(h);
 }
 
 extern "C" int gbenv_reset_host(gbenv *h, const uint8_t *mask, int max_episode_steps, double reward_scale, uint8_t *obs) {
@@ -493,11 +626,16 @@ extern "C" int gbenv_reset_host(gbenv *h, const uint8_t *mask, int max_episode_s
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     // rows of envs that are not reset keep the caller's bytes: stage the caller's buffer in first
-    if (mask) CK(cudaMemcpyAsync(h->d_obs, obs, (size_t)h->n * GBENV_OBS_BYTES, cudaMemcpyHostToDevice, h->stream));
-    rc = gbenv_reset(h, mask, max_episode_steps, reward_scale, h->d_obs, GBENV_OBS_BYTES, h->stream);
+    while (h->fetched < h->submitted) {
+        rc = gbenv_fetch_host(h);
+        if (rc) return rc;
+    }
+    cudaStream_t st = own(h);
+    if (mask) CK(cudaMemcpyAsync(h->d_obs[0], obs, (size_t)h->n * GBENV_OBS_BYTES, cudaMemcpyHostToDevice, st));
+    rc = gbenv_reset(h, mask, max_episode_steps, reward_scale, h->d_obs[0], GBENV_OBS_BYTES, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(obs, h->d_obs, (size_t)h->n * GBENV_OBS_BYTES, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(obs, h->d_obs[0], (size_t)h->n * GBENV_OBS_BYTES, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return GBENV_OK;
 }
 
@@ -521,6 +659,7 @@ extern "C" int gbenv_counts_map(gbenv *h, int env, int32_t *map_host) {
     if (!h || env < 0 || env >= h->n || !map_host) return fail(h, GBENV_E_ARG, "gbenv_counts_map: bad argument");
     if (!h->w.counts_map && !h->w.cm_hash) return fail(h, GBENV_E_ARG, "gbenv_counts_map: exploration map tracking is disabled (GBENV_COUNTS_MAP=0)");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     CK(cudaStreamSynchronize(h->stream));
     if (!h->w.counts_map) {  // sparse: rebuild the dense image from this env's hash entries
         std::vector<uint2> tab((size_t)h->w.cm_cap);
@@ -546,6 +685,7 @@ __global__ void k_count_faults(DevArrays d, WrapArrays w, unsigned long long *ou
 extern "C" int gbenv_get_counters(gbenv *h, gbenv_counters_t *out) {
     if (!h || !out) return fail(h, GBENV_E_ARG, "gbenv_get_counters: bad argument");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     CK(cudaMemsetAsync(h->d_counters + 3, 0, sizeof(unsigned long long), h->stream));
     k_count_faults<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->d, h->w, h->d_counters + 3);
     CK(cudaGetLastError());
@@ -583,6 +723,7 @@ extern "C" int gbenv_kernel_time_total(gbenv *h, int which, double *ms_total, ui
 extern "C" int gbenv_get_core_extra(gbenv *h, int env, gbenv_core_extra_t *out) {
     if (!h || env < 0 || env >= h->n || !out) return fail(h, GBENV_E_ARG, "gbenv_get_core_extra: bad argument");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     CK(cudaStreamSynchronize(h->stream));
     uint32_t lcd2 = 0, joy = 0, in = 0;
     int tile = env >> 5, lane = env & 31;
@@ -599,6 +740,7 @@ extern "C" int gbenv_get_core_extra(gbenv *h, int env, gbenv_core_extra_t *out) 
 extern "C" int gbenv_debug_render_frame(gbenv *h, int env) {
     if (!h || env < 0 || env >= h->n) return fail(h, GBENV_E_ARG, "gbenv_debug_render_frame: bad argument");
     CK(cudaSetDevice(h->device));
+    own(h);  // ordered after whatever was last queued on this handle, on any stream
     k_debug_render_frame<<<1, 1, 0, h->stream>>>(h->d, env);
     h->launches++;
     CK(cudaGetLastError());

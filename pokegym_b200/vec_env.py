@@ -59,6 +59,26 @@ def _lib() -> _capi.GbEnvLib:
     return _LIB
 
 
+def _default_state() -> Optional[Path]:
+    """The save-state pokegym.Environment falls back to when state_path is None (environment.py:119-120 loads the packaged
+    current_state/Bulbasaur.state): $POKEGYM_STATE, else that file inside an installed / checked-out pokegym package."""
+    env = os.environ.get("POKEGYM_STATE")
+    if env and Path(env).exists():
+        return Path(env)
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("pokegym")
+        if spec and spec.origin:
+            p = Path(spec.origin).parent / "current_state" / "Bulbasaur.state"
+            if p.exists():
+                return p
+    except Exception:
+        pass
+    p = Path("/root/reference/pokegym/current_state/Bulbasaur.state")
+    return p if p.exists() else None
+
+
 def _read_rom(rom_path: Union[str, os.PathLike, bytes]) -> bytes:
     if isinstance(rom_path, (bytes, bytearray)):
         return bytes(rom_path)
@@ -83,7 +103,8 @@ class VecEnvironment:
     """
 
     def __init__(self, num_envs: int, rom_path, state_paths: Union[None, str, bytes, Sequence] = None, device="cuda:0", rollout=None,
-                 auto_reset: bool = False, max_episode_steps: int = 20480, reward_scale: float = 4.0, boot_frames: int = 60):
+                 auto_reset: bool = False, max_episode_steps: int = 20480, reward_scale: float = 4.0, boot_frames: int = 60,
+                 validate_actions: bool = False):
         import torch
 
         self.torch = torch
@@ -96,15 +117,17 @@ class VecEnvironment:
         self.action_space = Discrete(_capi.NUM_ACTIONS)
         self.max_episode_steps, self.reward_scale, self.auto_reset = int(max_episode_steps), float(reward_scale), bool(auto_reset)
         self.rollout = rollout
+        self.validate_actions = bool(validate_actions)  # off by default: the check is a device->host sync; the kernel masks actions with & 7
         self._t = 0
         with torch.cuda.device(self.device):
             self._obs = torch.zeros((self.num_envs, *OBS_SHAPE), dtype=torch.uint8, device=self.device)
             self._reward = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
             self._done = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            self._done_prev = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
             self._info = torch.zeros((self.num_envs, _capi.INFO_SCALARS), dtype=torch.float64, device=self.device)
         if state_paths is None:
             # no save-state: boot the ROM for a few frames so every env sits in its main loop
-            self.handle.tick(boot_frames, True)
+            self.handle.tick(boot_frames, True, stream=self._stream())
         else:
             blobs = [state_paths] if isinstance(state_paths, (str, bytes, os.PathLike)) else list(state_paths)
             tids = [self.handle.add_state_template(b if isinstance(b, bytes) else Path(b).read_bytes()) for b in blobs]
@@ -123,8 +146,12 @@ class VecEnvironment:
     def _obs_target(self):
         if self.rollout is None:
             return self._obs
-        t = self.rollout[self._t % self.rollout.shape[0]]
-        return t
+        r = self.rollout
+        ok = (self.torch.is_tensor(r) and r.dtype == self.torch.uint8 and r.device == self.device and r.is_contiguous() and r.dim() >= 3
+              and r.shape[1] == self.num_envs and r[0, 0].numel() == _capi.OBS_BYTES)
+        if not ok:  # raw pointers cross the C ABI: a wrong layout would be out-of-bounds device writes, not an exception
+            raise ValueError(f"rollout must be a contiguous uint8 tensor [T, {self.num_envs}, 72, 80, 4] (or [T, N, 23040]) on {self.device}")
+        return r[self._t % r.shape[0]]
 
     # -- API -----------------------------------------------------------------
     def reset(self, mask=None, max_episode_steps: Optional[int] = None, reward_scale: Optional[float] = None):
@@ -134,9 +161,18 @@ class VecEnvironment:
         if reward_scale is not None:
             self.reward_scale = float(reward_scale)
         obs = self._obs_target()
-        m = None if mask is None else np.ascontiguousarray(mask.cpu().numpy() if hasattr(mask, "cpu") else mask, dtype=np.uint8)
-        self.handle.reset(obs, mask=m, max_episode_steps=self.max_episode_steps, reward_scale=self.reward_scale, obs_stride=_capi.OBS_BYTES,
-                          stream=self._stream())
+        torch = self.torch
+        if mask is not None and not torch.is_tensor(mask):
+            mask = torch.as_tensor(np.ascontiguousarray(mask, dtype=np.uint8), device=self.device)
+        if mask is not None:  # a device mask (e.g. the done vector): the reset stays on the device, no host round trip
+            if mask.dtype == torch.bool:
+                mask = mask.to(torch.uint8)
+            if mask.dtype != torch.uint8 or mask.device != self.device or not mask.is_contiguous() or mask.numel() != self.num_envs:
+                mask = mask.to(device=self.device, dtype=torch.uint8).contiguous().view(-1)
+                if mask.numel() != self.num_envs:
+                    raise ValueError(f"reset mask must have {self.num_envs} entries")
+        self.handle.reset_dev(obs, mask_dev=mask, max_episode_steps=self.max_episode_steps, reward_scale=self.reward_scale,
+                              obs_stride=_capi.OBS_BYTES, stream=self._stream())
         return obs.view(self.num_envs, *OBS_SHAPE), {}
 
     def step(self, actions):
@@ -146,14 +182,20 @@ class VecEnvironment:
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
         if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
+        if self.validate_actions and bool((actions >= _capi.NUM_ACTIONS).any()):  # the reference raises IndexError (ACTIONS[action])
+            raise IndexError("action out of range 0..7")
         self._t += 1
         obs = self._obs_target()
         self.handle.step(actions, obs, self._reward, self._done, obs_stride=_capi.OBS_BYTES, stream=self._stream())
         done = self._done.bool()
         if self.auto_reset:
-            d = self._done.cpu().numpy()
-            if d.any():
-                self.reset(mask=d)
+            # envs that just finished are reset on the device, masked by the done vector the step wrote: their row of `obs`
+            # becomes the reset observation, as a vectoriser that resets after `done` would deliver it (no host round trip)
+            self._done_prev.copy_(self._done)
+            self.handle.reset_dev(obs, mask_dev=self._done_prev, max_episode_steps=self.max_episode_steps, reward_scale=self.reward_scale,
+                                  obs_stride=_capi.OBS_BYTES, stream=self._stream())
         return obs.view(self.num_envs, *OBS_SHAPE), self._reward, done, done, {}
 
     @staticmethod
@@ -163,7 +205,7 @@ class VecEnvironment:
         return obs[..., 2:]
 
     def info(self):
-        """Per-env info rows: float64 [N, 64]; column names in pokegym_b200.info.INFO_NAMES."""
+        """Per-env info rows: float64 [N, 72] (GBENV_INFO_SCALARS); column names in pokegym_b200.info.INFO_NAMES."""
         self.handle.get_info(self._info, stream=self._stream())
         return self._info
 
@@ -189,6 +231,10 @@ class VecEnvironment:
     def save_state(self, env: int = 0) -> bytes:
         return self.handle.save_state(env)
 
+    def load_state(self, blob: bytes, env_ids=None):
+        """PyBoy.load_state for the listed envs (None: all): pyboy_binding.load_pyboy_state (:65-69)."""
+        self.handle.load_template(self.handle.add_state_template(blob), env_ids)
+
     def close(self):
         self.handle.close()
 
@@ -199,6 +245,13 @@ class Environment:
     def __init__(self, rom_path="pokemon_red.gb", state_path=None, headless=True, save_video=False, quiet=False, verbose=False, device="cuda:0", **kwargs):
         if save_video or not headless:
             raise NotImplementedError("video / SDL2 window output is out of scope (SURVEY.md section 8b non-goals)")
+        if state_path is None and not isinstance(rom_path, (bytes, bytearray)):
+            # environment.py:119-120: the reference falls back to its packaged current_state/Bulbasaur.state.  With a ROM
+            # given as bytes (the synthetic test ROMs) there is no such convention and the ROM is booted instead.
+            state_path = _default_state()
+            if state_path is None:
+                raise FileNotFoundError("no state_path given and pokegym's default current_state/Bulbasaur.state was not found "
+                                        "(set POKEGYM_STATE or pass state_path)")
         self.vec = VecEnvironment(1, rom_path, state_paths=state_path, device=device)
         self.observation_space = self.vec.observation_space
         self.action_space = self.vec.action_space
@@ -229,6 +282,23 @@ class Environment:
     def render(self):
         """The observation the last reset()/step() returned (environment.py:256-274 rebuilds the same array)."""
         return self._last_obs
+
+    # environment.py:208-227: save_state / load_first_state / load_last_state / load_random_state over self.initial_states
+    def save_state(self):
+        if not hasattr(self, "initial_states"):
+            self.initial_states = []
+        self.initial_states.append(self.vec.save_state(0))
+
+    def load_first_state(self):
+        return self.initial_states[0]
+
+    def load_last_state(self):
+        return self.initial_states[-1]
+
+    def load_random_state(self):
+        import random
+
+        return self.initial_states[random.randrange(len(self.initial_states))]
 
     def close(self):
         self.vec.close()
