@@ -326,6 +326,7 @@ def run_leg(lib, rom, E, steps, warmup, preroll, dev, device_id, seed=7, state_p
 
 LEGS = {
     # name: (rom, envs, steps, warmup, preroll, mixed states)
+    "main_4096": ("pokelike", 4096, 40, 5, 150, False),  # the headline workload as a leg (tools/gpu_exp2.sh: lanes sweeps)
     "envs_32768": ("pokelike", 32768, 20, 5, 100, False),
     "busy_4096": ("busy", 4096, 12, 3, 30, False),
     "timer_4096": ("pokelike_timer", 4096, 20, 5, 60, False),
@@ -537,7 +538,7 @@ def main():
                          "lanes_active_per_warp_instr": counters["lanes_active"], "warp_instr_per_s": wi / (run_ms / 1000.0),
                          "peak_warp_instr_per_s": issue_peak, "frac": wi / (run_ms / 1000.0) / issue_peak,
                          "ncu_issue_active_pct": counters.get("issue_active_pct"), "source": counters.get("source")}
-    want = [] if args.legs == "none" else (list(LEGS) if args.legs == "all" else [x for x in args.legs.split(",") if x in LEGS])
+    want = [] if args.legs == "none" else ([x for x in LEGS if x != "main_4096"] if args.legs == "all" else [x for x in args.legs.split(",") if x in LEGS])
     if world == 1 and want:
         h.close()
         del rollout

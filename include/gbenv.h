@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GBENV_ABI_VERSION 3 /* 2: info row widened from 64 to 72 doubles; 3: gbenv_reset_dev, gbenv_submit_host / gbenv_fetch_host */
+#define GBENV_ABI_VERSION 3 /* 2: info row widened from 64 to 72 doubles; 3: gbenv_reset_dev, gbenv_submit_host / gbenv_fetch_host, gbenv_check, gbenv_step_masked */
 
 #define GBENV_STATE_BYTES 142610 /* PyBoy v9 save-state length              */
 #define GBENV_OBS_H 72           /* environment.py:154-166: (144//2, 160//2, 4) uint8       */
@@ -65,6 +65,12 @@ const char *gbenv_last_error(const gbenv_t *h);
 int gbenv_num_envs(const gbenv_t *h);
 int gbenv_abi_version(void);
 int gbenv_sync(gbenv_t *h); /* cudaStreamSynchronize on the handle's stream */
+/* gbenv_sync + the sticky error state of the exploration storage.  Visited bitmaps (seen_coords / screen_memory,
+ * environment.py:256-274, :1344) and heat maps (counts_map, :648-679) are paged out of pools shared by all envs, so any
+ * env may hold all 248 maps; should a pool run dry the affected env stops matching the reference, which is an ERROR:
+ * this call, and every gbenv_step / gbenv_reset* issued once the condition has reached the host (at most two calls
+ * later, no synchronisation involved), return GBENV_E_NOMEM with the pool named in gbenv_last_error.             */
+int gbenv_check(gbenv_t *h);
 /* Tuning knob: envs carried by each warp of the emulation kernel (1..32).  The default is
  * chosen from n_envs and the SM count so that a small batch still fills the GPU with warps.        */
 int gbenv_set_lanes_per_warp(gbenv_t *h, int lanes);
@@ -114,6 +120,12 @@ int gbenv_reset_dev(gbenv_t *h, const uint8_t *mask_dev, int max_episode_steps, 
  *   (terminated == truncated, environment.py:1613,1812).  No host round trip.                   */
 int gbenv_step(gbenv_t *h, const uint8_t *actions_dev, uint8_t *obs_dev, size_t obs_stride,
                double *reward_dev, uint8_t *done_dev, void *stream);
+/* The same for the envs with skip_dev[e] == 0 only (skip_dev NULL: all).  A skipped env is not emulated: its state, info row
+ * and observation row stay untouched and it reports reward 0, done 0.  This is what a vectoriser needs that resets an env on
+ * the call AFTER its `done` and ignores that call's action for it (PufferLib's Serial / Multiprocessing backends):
+ * gbenv_reset_dev(mask = previous done) followed by gbenv_step_masked(skip = the same mask).                          */
+int gbenv_step_masked(gbenv_t *h, const uint8_t *actions_dev, const uint8_t *skip_dev, uint8_t *obs_dev, size_t obs_stride,
+                      double *reward_dev, uint8_t *done_dev, void *stream);
 /* Same call with HOST buffers (pinned or pageable): copies in, steps, copies out, synchronises.
  * This is the reference-facing entry point a pokegym worker would call.                         */
 int gbenv_step_host(gbenv_t *h, const uint8_t *actions_host, uint8_t *obs_host, double *reward_host,

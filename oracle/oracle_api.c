@@ -86,6 +86,7 @@ int oracle_destroy(oracle *h) {
 const char *oracle_last_error(const oracle *h) { return h ? h->err : g_err; }
 int oracle_num_envs(const oracle *h) { return h ? h->n : GBENV_E_ARG; }
 int oracle_sync(oracle *h) { return h ? GBENV_OK : GBENV_E_ARG; }
+int oracle_check(oracle *h) { return h ? GBENV_OK : GBENV_E_ARG; } /* the oracle keeps whole maps per env: nothing to exhaust */
 
 int oracle_add_state_template(oracle *h, const uint8_t *blob, size_t len, int *id_out) {
     if (!h || !blob || !id_out) return GBENV_E_ARG;
@@ -188,6 +189,7 @@ typedef struct run_ctx {
     size_t obs_stride;
     double *reward;
     uint8_t *done;
+    const uint8_t *skip; /* oracle_step_masked: envs that sit this step out */
 } run_ctx;
 
 static void fn_run_action(oracle *h, int e, void *ctx) {
@@ -203,6 +205,11 @@ static void fn_step(oracle *h, int e, void *ctx) {
     run_ctx *c = (run_ctx *)ctx;
     oracle_env *E = &h->envs[e];
     int d = 0;
+    if (c->skip && c->skip[e]) { /* not stepped: reward 0, done 0, observation row untouched */
+        c->reward[e] = 0.0;
+        c->done[e] = 0;
+        return;
+    }
     c->reward[e] = pg_step(&E->wrap, &E->core, c->actions[e], c->obs + (size_t)e * c->obs_stride, &d);
     c->done[e] = (uint8_t)d;
 }
@@ -210,7 +217,7 @@ static void fn_step(oracle *h, int e, void *ctx) {
 int oracle_run_action(oracle *h, const uint8_t *actions, int frame_skip, void *stream) {
     (void)stream;
     if (!h || !actions) return GBENV_E_ARG;
-    run_ctx c = {actions, frame_skip, 0, NULL, 0, NULL, NULL};
+    run_ctx c = {actions, frame_skip, 0, NULL, 0, NULL, NULL, NULL};
     par_for(h, fn_run_action, &c);
     return GBENV_OK;
 }
@@ -218,7 +225,7 @@ int oracle_run_action(oracle *h, const uint8_t *actions, int frame_skip, void *s
 int oracle_tick(oracle *h, int n_frames, int render, void *stream) {
     (void)stream;
     if (!h) return GBENV_E_ARG;
-    run_ctx c = {NULL, n_frames, render, NULL, 0, NULL, NULL};
+    run_ctx c = {NULL, n_frames, render, NULL, 0, NULL, NULL, NULL};
     par_for(h, fn_tick, &c);
     return GBENV_OK;
 }
@@ -268,12 +275,17 @@ int oracle_reset(oracle *h, const uint8_t *mask, int max_episode_steps, double r
     return GBENV_OK;
 }
 
-int oracle_step(oracle *h, const uint8_t *actions, uint8_t *obs, size_t obs_stride, double *reward, uint8_t *done, void *stream) {
+int oracle_step_masked(oracle *h, const uint8_t *actions, const uint8_t *skip, uint8_t *obs, size_t obs_stride, double *reward, uint8_t *done,
+                       void *stream) {
     (void)stream;
     if (!h || !actions || !obs || !reward || !done || obs_stride < GBENV_OBS_BYTES) return GBENV_E_ARG;
-    run_ctx c = {actions, 24, 0, obs, obs_stride, reward, done};
+    run_ctx c = {actions, 24, 0, obs, obs_stride, reward, done, skip};
     par_for(h, fn_step, &c);
     return GBENV_OK;
+}
+
+int oracle_step(oracle *h, const uint8_t *actions, uint8_t *obs, size_t obs_stride, double *reward, uint8_t *done, void *stream) {
+    return oracle_step_masked(h, actions, NULL, obs, obs_stride, reward, done, stream);
 }
 
 int oracle_step_host(oracle *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done) {

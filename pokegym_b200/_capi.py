@@ -62,6 +62,7 @@ _SIGS = {
     "last_error": ([C.c_void_p], C.c_char_p),
     "num_envs": ([C.c_void_p], C.c_int),
     "sync": ([C.c_void_p], C.c_int),
+    "check": ([C.c_void_p], C.c_int),
     "set_lanes_per_warp": ([C.c_void_p, C.c_int], C.c_int),
     "add_state_template": ([C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)], C.c_int),
     "load_template": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int], C.c_int),
@@ -79,6 +80,7 @@ _SIGS = {
     "submit_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "fetch_host": ([C.c_void_p], C.c_int),
     "step": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    "step_masked": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "step_host": ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "reset_host": ([C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p], C.c_int),
     "get_info": ([C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
@@ -223,6 +225,11 @@ class Handle:
     def step(self, actions, obs, reward, done, obs_stride: int = OBS_BYTES, stream: int = 0):
         self._check(self.lib.step(self._h, _ptr(actions), _ptr(obs), int(obs_stride), _ptr(reward), _ptr(done), C.c_void_p(stream)), "step")
 
+    def step_masked(self, actions, skip, obs, reward, done, obs_stride: int = OBS_BYTES, stream: int = 0):
+        """Environment.step for the envs with skip[e] == 0; the others sit the step out (reward 0, done 0, obs row untouched)."""
+        self._check(self.lib.step_masked(self._h, _ptr(actions), _ptr(skip), _ptr(obs), int(obs_stride), _ptr(reward), _ptr(done), C.c_void_p(stream)),
+                    "step_masked")
+
     def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
         self._check(self.lib.step_host(self._h, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done)), "step_host")
 
@@ -244,6 +251,10 @@ class Handle:
     # -- diagnostics ---------------------------------------------------------
     def sync(self):
         self._check(self.lib.sync(self._h), "sync")
+
+    def check(self):
+        """sync + raise if a pool of the exploration storage (visited bitmaps / heat maps) ran dry"""
+        self._check(self.lib.check(self._h), "check")
 
     def set_lanes_per_warp(self, lanes: int):
         self._check(self.lib.set_lanes_per_warp(self._h, int(lanes)), "set_lanes_per_warp")

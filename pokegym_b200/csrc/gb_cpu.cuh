@@ -21,6 +21,24 @@
 #include "gb_device.cuh"
 #include "gb_predecode.h"
 
+// tuning switches of the fast loop (tools/build_variants.sh builds A/B libraries; the defaults are the shipped choice)
+#ifndef GB_OPT_SYNCWARP
+#define GB_OPT_SYNCWARP 1       // explicit __syncwarp re-convergence in front of the write-back
+#endif
+#ifndef GB_OPT_DECLINE_FLAG
+#define GB_OPT_DECLINE_FLAG 1   // declines set a flag and leave at ONE exit (structured regions) instead of returning early
+#endif
+#ifndef GB_OPT_ONE_BODY
+#define GB_OPT_ONE_BODY 1       // one inlined instance of the instruction body for ROM and HRAM code
+#endif
+#ifndef GB_OPT_FLAG_DISPATCH
+#define GB_OPT_FLAG_DISPATCH 1  // INC/DEC and the arithmetic group are recognised by descriptor flag bits, not by handler id
+#endif
+
+#if !defined(GB_TRACE_SLOT)
+#define GB_TRACE_SLOT(kind, phys, dx, dw)  // host-side convergence study only (tests/hostsim, -DGB_SLOT_TRACE)
+#endif
+
 __constant__ uint4 c_base_desc[512];  // per-opcode base descriptors (pd_build_base), uploaded once per process
 
 #define MODE_ATTN 0x8000u   // pending interrupt / HALT / PyBoy's interrupt_queued latch: the tick starts in cpu_attention
@@ -141,11 +159,20 @@ __device__ __forceinline__ bool fast_stack_push(uint32_t sp) { return sp - 0xC00
 // One instruction, given its control word.  FAST: returns false -- having changed nothing -- when the instruction needs
 // anything outside the fast set; `mode` is only read.  !FAST: always completes (full bus, every opcode).
 // Outputs: r (registers incl. pc), rom_off (bank switches), cyc, mode (HALT).
+// FAST: `grp` is the set of lanes that entered this loop iteration together (__activemask at its top) and `declined` may come in
+// already set (no descriptor could be fetched).  Every one of those lanes reaches the __syncwarp(grp) between the handler
+// and the write-back -- the body has no exit in front of it -- so the write-back, the stores and the loop tail are executed
+// once per warp again, however many handlers the lanes went through.  (nvcc gives the handler switch no reconvergence point of
+// its own: measured 2.5 executions of the write-back per iteration with 2.9 of 8 lanes each.)
 template <bool FAST>
 __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &mode, uint32_t &cyc, uint8_t *memb,
-                                         const uint8_t *rom, uint32_t bank_mask) {
+                                         const uint8_t *rom, uint32_t bank_mask, unsigned grp = 0, bool declined = false) {
     uint32_t bcde = r.bcde, hlaf = r.hlaf, sp = r.sp;
-    bool declined = false;
+#if GB_OPT_DECLINE_FLAG
+#define FAST_DECLINE() declined = true
+#else
+#define FAST_DECLINE() return false
+#endif
     auto rd8 = [&](uint32_t a) -> uint32_t {  // Motherboard.getitem; FAST: WRAM (+ echo), ROM and HRAM, else decline
         if (FAST) {
             if (a - 0xC000u < 0x3E00u) return memb[mem_offset(MEM_WRAM + (a & 0x1FFF))];
@@ -161,18 +188,20 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     uint32_t v = gb_prmt(bcde, hlaf, w);  // byte 0 = source register (upper bytes: don't care)
     if (w & PDF_IMM) v = d.y & 0xFFFFu;
     uint32_t wa = 0, wt = 0;  // store address; FAST: its classified target
-    if (FAST && h >= H_RARE) return false;  // rare opcodes, on-the-fly decode
+    // FAST: whatever makes the body decline only sets `declined`; the one exit is in front of the write-back, so every
+    // divergent region below is single-entry / single-exit and the lanes of a warp re-converge behind each of them
+    if (FAST && h >= H_RARE) FAST_DECLINE();  // rare opcodes, on-the-fly decode
     if (w & (PDF_RD | PDF_WR)) {
         wa = (w & PDF_AIMM) ? (d.y & 0xFFFFu) : (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu);
         if (w & PDF_ASP) wa = sp;
         if (FAST && (w & PDF_WR)) {
             wt = fast_store_target(wa);
-            if (wt == FAST_WR_NONE) return false;
+            if (wt == FAST_WR_NONE) FAST_DECLINE();
         }
         if (w & PDF_RD) {
             v = rd8(wa);
             if (w & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
-            if (FAST && declined) return false;
+            if (FAST && !GB_OPT_DECLINE_FLAG && declined) return false;
         }
     }
     // ---- handler
@@ -181,16 +210,16 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     cyc = d.x >> 24;
 #define PAIR_OPERAND() (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu)
     // The most frequent handlers are tested first, one compare each; the rest share a switch.
-    if (w & PDF_MOV) {
+    if ((w & PDF_MOV) || (FAST && GB_OPT_DECLINE_FLAG && declined)) {
         // plain moves (a third of all instructions) are done: rv = v
     } else if (w & PDF_JUMP) {
         if (((f ^ ex) & op) == 0) { next_pc = imm16; cyc += ex & 0xF; }
-    } else if (h == H_INCDEC) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
+    } else if (GB_OPT_FLAG_DISPATCH ? (w & PDF_INCDEC) != 0 : h == H_INCDEC) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
         const uint32_t b = v & 0xFF, sum = b + op, res = sum & 0xFF;
         const uint32_t nf = (f & FLAG_C) | ((((b ^ op ^ sum) & 0x10) << 1) ^ ex) | (res == 0 ? FLAG_Z : 0);
         rv = res | (nf << 8);
         wv = res;
-    } else if (h == H_ARITH) {  // branch-free: a subtraction adds the complement and inverts the carries
+    } else if (GB_OPT_FLAG_DISPATCH ? (w & PDF_ARITH) != 0 : h == H_ARITH) {  // branch-free: a subtraction adds the complement and inverts the carries
         const uint32_t a = (hlaf >> 16) & 0xFF, x = (v & 0xFF) ^ ex;
         const uint32_t sum = a + x + ((((f >> 4) & op) ^ ex) & 1);  // carry in for ADC / SBC only
         const uint32_t res = sum & 0xFF;
@@ -213,7 +242,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     }
     case H_CALL: {
         if (((f ^ ex) & op) == 0) {  // high byte at SP-1 first, then low byte at SP-2
-            if (FAST && !fast_stack_push(sp)) return false;
+            if (FAST && !fast_stack_push(sp)) FAST_DECLINE();
             wa = (sp - 1) & 0xFFFF;
             wv = gb_prmt(next_pc, 0, 0x4401);
             wn = 2;
@@ -233,7 +262,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         break;
     }
     case H_PUSH:
-        if (FAST && !fast_stack_push(sp)) return false;
+        if (FAST && !fast_stack_push(sp)) FAST_DECLINE();
         wa = (sp - 1) & 0xFFFF;
         wv = gb_prmt(PAIR_OPERAND(), 0, 0x4401);
         wn = 2;
@@ -320,6 +349,11 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     }
     }
 #undef PAIR_OPERAND
+    if (FAST) {
+        if (GB_OPT_SYNCWARP) __syncwarp(grp);
+        if (declined) return false;  // nothing has been changed
+    }
+#undef FAST_DECLINE
     // ---- register write-back (uniform)
     r.bcde = gb_prmt(bcde, rv, d.z);
     r.hlaf = gb_prmt(hlaf, rv, d.z >> 16);
@@ -400,13 +434,39 @@ __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
         // stack on every iteration).  Left when the deadline is reached or an instruction needs the slow tick.
         for (;;) {
             uint32_t cyc;
-            if (!((r.pc | mode) & (0x8000u | MODE_POST))) {  // ROM code, nothing pending, not halted, TIMA stopped
-                if (!cpu_exec<true>(m, __ldg(cx.rom_dec + (r.pc + (r.pc >> 14) * rom_off)), r, rom_off, mode, cyc, memb, rom, cx.bank_mask)) break;
-            } else if (!(mode & (MODE_ATTN | MODE_POST)) && r.pc - 0xFF80u < 0x7Du) {
-                if (!cpu_exec<true>(m, cpu_decode_hram(memb, r.pc), r, rom_off, mode, cyc, memb, rom, cx.bank_mask)) break;
+            const unsigned grp = GB_OPT_SYNCWARP ? __activemask() : 0u;
+            // ONE instance of the instruction body: the descriptor comes from the pre-decoded ROM table or, for the HRAM stub,
+            // from an inline decode -- lanes running either kind of code meet again in front of cpu_exec.  A lane that has to
+            // leave the loop (interrupt pending, HALT, running TIMA, code in other RAM) goes through the body as `declined`.
+            uint4 d = make_uint4(H_SLOW, 0, 0x32103210u, 0);
+            bool leave = false;
+            const uint32_t pc = r.pc;
+#if GB_OPT_ONE_BODY
+            if (!((pc | mode) & (0x8000u | MODE_POST))) {  // ROM code, nothing pending, not halted, TIMA stopped
+                d = __ldg(cx.rom_dec + (pc + (pc >> 14) * rom_off));
+            } else if (!(mode & (MODE_ATTN | MODE_POST)) && pc - 0xFF80u < 0x7Du) {
+                d = cpu_decode_hram(memb, pc);
+            } else {
+#if GB_OPT_DECLINE_FLAG
+                leave = true;
+#else
+                break;
+#endif
+            }
+            if (!cpu_exec<true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, grp, leave)) break;
+#else
+            (void)leave;
+            if (!((pc | mode) & (0x8000u | MODE_POST))) {
+                d = __ldg(cx.rom_dec + (pc + (pc >> 14) * rom_off));
+                if (!cpu_exec<true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, grp, false)) break;
+            } else if (!(mode & (MODE_ATTN | MODE_POST)) && pc - 0xFF80u < 0x7Du) {
+                d = cpu_decode_hram(memb, pc);
+                if (!cpu_exec<true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, grp, false)) break;
             } else {
                 break;
             }
+#endif
+            GB_TRACE_SLOT(0, pc < 0x8000u ? pc + (pc >> 14) * rom_off : (0xF00000u | pc), d.x, d.w);
             n_instr++;
             rem -= (int)cyc;
             if (rem <= 0) goto deadline;
@@ -418,6 +478,7 @@ __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
             m.bcde = r.bcde; m.hlaf = r.hlaf; m.sp = r.sp; m.pc = r.pc; m.n_instr = n_instr;
             time_sync(m, rem);
             if (m.lazy && (int)(m.clock - m.target) >= 0) lcd_catch_up(m);
+            GB_TRACE_SLOT(1, m.pc < 0x8000u ? m.pc + (m.pc >> 14) * m.rom_off : (0xF00000u | m.pc), 0, 0);
             const uint32_t cyc = cpu_tick_slow(m, cx.rom_dec, cx.bank_mask);
             r.bcde = m.bcde; r.hlaf = m.hlaf; r.sp = m.sp; r.pc = m.pc; n_instr = m.n_instr; rom_off = m.rom_off;
             memb = m.memb; rom = m.rom;

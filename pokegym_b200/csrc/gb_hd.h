@@ -36,7 +36,8 @@ static gb_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}
 #define __restrict__
 #define __launch_bounds__(...)
 static inline void __syncthreads() {}
-static inline void __syncwarp() {}
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) {}
+static inline unsigned __activemask() { return 1u; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s) {
     uint64_t src = (uint64_t)a | ((uint64_t)b << 32);

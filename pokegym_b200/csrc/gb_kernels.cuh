@@ -19,6 +19,7 @@ __constant__ int c_action_button[8] = {3, 1, 0, 2, 4, 5, 7, 6};
 struct RunParams {
     DevArrays d;
     const uint8_t *actions;  // may be null: plain ticks without input
+    const uint8_t *skip;     // may be null; envs with skip[e] != 0 are not run (gbenv_step_masked)
     int n_frames;
     int render_mode;  // 0: renderer disabled, 1: enabled on every frame, 2: enabled on the last frame only
     int release_frame;  // frame index at which the button is released (8 in the reference)
@@ -56,6 +57,7 @@ __device__ __forceinline__ void run_frames_env(Machine &m, const RunParams &p, i
         bool done = m.frame_done;
         m.frame_done = 0;
         while (!done) {
+            GB_TRACE_SLOT(2, 0, 0, 0);  // the lanes of a warp re-converge here
             if (m.halted && !(m.iq | (m.iflag & m.ie & 0x1F) | (m.tmr & 0x04000000u)) && (m.lcdc & 0x80)) {
                 // Quiet HALT (nothing pending, TIMA stopped): CPU.tick is a no-op and Motherboard.tick jumps from LCD mode
                 // change to mode change; only a hard one (VBlank entry, a rendered HBlank) can end the HALT or the frame,
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
     const int warp = (blockIdx.x * STEP_THREADS + tid) >> 5, wl = tid & 31;
     if (wl >= p.lanes) return;  // partial-warp mode: only the first `lanes` threads of each warp carry an env
     const int env = warp * p.lanes + wl;
-    if (env >= p.d.n_envs) return;
+    if (env >= p.d.n_envs || (p.skip && p.skip[env])) return;
     const int tile = env >> 5, lane = env & 31;
     const uint32_t nslots = (STEP_THREADS / 32) * p.lanes, si = (tid >> 5) * p.lanes + wl;
     EnvSlot &slot = *(EnvSlot *)((char *)s_env_slots + (size_t)si * ENV_SLOT_STRIDE);

@@ -63,6 +63,8 @@ enum {
 #define PDF_RETI 0x0400u  // RETI: IME = 1
 #define PDF_MOV 0x0800u   // handler is H_MOV (tested as a flag so that the dispatch of plain moves is one predicate, not a switch level)
 #define PDF_JUMP 0x1000u  // handler is H_JUMP
+#define PDF_INCDEC 0x2000u  // handler is H_INCDEC
+#define PDF_ARITH 0x4000u   // handler is H_ARITH
 
 #define PD_H(x) ((x) & 0xFFu)
 #define PD_OP(x) (((x) >> 8) & 0xFFu)
@@ -110,7 +112,8 @@ static inline pd_desc_t pd_b_done(const pd_builder *b) {
     d.x = b->h | (b->op << 8) | (b->ex << 16) | (b->cyc << 24);
     d.y = (b->imm & 0xFFFFu) | (b->len << 16) | (b->kind << 24);
     d.z = b->sel_lo | (b->sel_hi << 16);
-    d.w = (b->srcsel & 0xFu) | (b->flags & 0xFFF0u) | (b->h == H_MOV ? PDF_MOV : 0u) | (b->h == H_JUMP ? PDF_JUMP : 0u) | (b->asel << 16);
+    d.w = (b->srcsel & 0xFu) | (b->flags & 0xFFF0u) | (b->h == H_MOV ? PDF_MOV : 0u) | (b->h == H_JUMP ? PDF_JUMP : 0u) |
+          (b->h == H_INCDEC ? PDF_INCDEC : 0u) | (b->h == H_ARITH ? PDF_ARITH : 0u) | (b->asel << 16);
     return d;
 }
 

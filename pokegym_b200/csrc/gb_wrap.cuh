@@ -19,9 +19,23 @@
 #define WRAP_MAPS 248
 #define WRAP_CUT_COORDS 64
 #define VIS_ROW_WORDS 8                       // 256 columns / 32
-#define VIS_MAP_WORDS (256 * VIS_ROW_WORDS)   // one map: 256 rows x 256 bits = 8 KiB
+#define VIS_BAND_ROWS 64                      // a visited-bitmap page covers 64 rows x 256 columns of one map = 2 KiB
+#define VIS_BANDS 4
+#define VIS_PAGE_WORDS (VIS_BAND_ROWS * VIS_ROW_WORDS)
+#define VIS_PT_ENTRIES (WRAP_MAPS * VIS_BANDS)  // page-table entries per env
 #define COUNTS_H 444
 #define COUNTS_W 436
+#define CM_BLOCK 16                           // heat-map blocks of 16 x 16 cells = 1 KiB
+#define CM_BLOCKS_X ((COUNTS_W + CM_BLOCK - 1) / CM_BLOCK)
+#define CM_BLOCKS_Y ((COUNTS_H + CM_BLOCK - 1) / CM_BLOCK)
+#define CM_DIR_ENTRIES (CM_BLOCKS_X * CM_BLOCKS_Y)
+// WrapArrays.ctl words
+#define CTL_VIS_FREE 0    // number of free visited-bitmap pages (top of the free stack)
+#define CTL_CM_NEXT 1     // next never-used heat-map block
+#define CTL_ERROR 2       // sticky error bits, see GBENV_POOL_*
+#define POOL_ERR_VISITED 1u
+#define POOL_ERR_HEATMAP 2u
+#define POOL_ERR_CUT_COORDS 4u
 
 struct CutCoord {
     int32_t x, y, map, pad;
@@ -32,7 +46,6 @@ struct CutCoord {
 struct WrapState {
     // env-lifetime
     int32_t reset_count, is_dead, last_map, initial_template;
-    int32_t cm_used, cm_pad;  // entries in this env's sparse heat map
     double item_reward[5];
     long long coord_sum;  // running np.sum(counts_map)
     // per-episode
@@ -42,21 +55,28 @@ struct WrapState {
     int32_t n_seen_maps, prev_map_n, death_count, last_party_size;
     int32_t hm_latch, cut, used_cut, n_cut_coords;
     int32_t n_cut_tiles, n_cut_state, seen_start_menu, seen_pokemon_menu;
-    int32_t seen_stats_menu, seen_bag_menu, last_map_id_plus1, n_slots;
+    int32_t seen_stats_menu, seen_bag_menu, last_map_id_plus1, pad0;
     int32_t reset_r, reset_c, reset_map, reset_pending;  // render() at reset marks a tile seen_coords does not hold
     int32_t cut_state[3][6];
     uint32_t seen_maps_bits[8], cut_tiles_bits[8], moves_bits[6];
-    uint8_t map_slot[WRAP_MAPS];
     CutCoord cut_coords[WRAP_CUT_COORDS];
 };
 
+// Exploration storage is paged: nothing is reserved per env, so ANY env can hold all 248 maps / the whole 444 x 436 heat map
+// as long as the shared pools last (they are sized to the batch or to a memory budget, gbenv.cu); a pool running dry is an
+// error (CTL_ERROR, reported by the next gbenv_step / gbenv_reset / gbenv_check), never a silent loss.
+//   visited bitmaps (seen_coords / screen_memory, environment.py:256-274, :1344): per env a page table of 248 maps x 4 row bands;
+//     pages come from a free stack and go back to it, zeroed, when the env is reset.
+//   heat map (counts_map, :648-679, env-lifetime): per env a directory of 28 x 28 blocks; blocks are bump-allocated, never freed.
 struct WrapArrays {
     WrapState *state;     // [n_envs]
-    uint32_t *visited;    // [n_envs][slots][VIS_MAP_WORDS]
-    int32_t *counts_map;  // dense heat maps [n_envs][444*436], or null when they do not fit (then cm_hash is used)
-    uint2 *cm_hash;       // sparse heat maps [n_envs][cm_cap]: {cell index + 1 (0 = empty), count}, linear probing
-    int cm_cap;           // power of two
-    int slots;
+    uint32_t *vis_pt;     // [n_envs][VIS_PT_ENTRIES]: page index + 1, 0 = no page yet
+    uint32_t *vis_pool;   // [vis_pages][VIS_PAGE_WORDS]
+    int32_t *vis_free;    // [vis_pages] stack of free page indices
+    uint32_t *cm_dir;     // [n_envs][CM_DIR_ENTRIES]: block index + 1, 0 = no block yet; null = heat maps switched off
+    int32_t *cm_pool;     // [cm_blocks][CM_BLOCK * CM_BLOCK]
+    int32_t *ctl;         // CTL_* words
+    int vis_pages, cm_blocks;
 };
 
 struct MapOffset { int16_t x, y, known; };
@@ -134,19 +154,41 @@ __device__ __forceinline__ void wrap_position(Machine &m, int &r, int &c, int &m
     if (map_n > 247) map_n = 247;
 }
 
-// visited bitmap: slot allocation on first visit of a map
-__device__ inline uint32_t *visited_map(const WrapArrays &w, WrapState &s, int env, int map_n, bool create) {
-    int slot = s.map_slot[map_n];
-    if (slot == 0xFF) {
+// visited bitmap: the 8 words of row r of map map_n, its page allocated on first use (nullptr: no page / pool exhausted)
+__device__ inline uint32_t *visited_row(const WrapArrays &w, WrapState &s, int env, int map_n, int r, bool create) {
+    uint32_t *e = w.vis_pt + (size_t)env * VIS_PT_ENTRIES + map_n * VIS_BANDS + (r / VIS_BAND_ROWS);
+    uint32_t pg = *e;
+    if (!pg) {
         if (!create) return nullptr;
-        if (s.n_slots >= w.slots) {
+        const int i = atomicSub(&w.ctl[CTL_VIS_FREE], 1);  // pops only in this kernel family; pushes only in k_vis_release
+        if (i <= 0) {
+            atomicAdd(&w.ctl[CTL_VIS_FREE], 1);
+            atomicOr((unsigned int *)&w.ctl[CTL_ERROR], POOL_ERR_VISITED);
             s.overflow = 1;
             return nullptr;
         }
-        slot = s.n_slots++;
-        s.map_slot[map_n] = (uint8_t)slot;
+        pg = (uint32_t)w.vis_free[i - 1] + 1;
+        *e = pg;
     }
-    return w.visited + ((size_t)env * w.slots + slot) * VIS_MAP_WORDS;
+    return w.vis_pool + (size_t)(pg - 1) * VIS_PAGE_WORDS + (r % VIS_BAND_ROWS) * VIS_ROW_WORDS;
+}
+
+// heat map cell (glob_r, glob_c) of env, its block allocated on first use
+__device__ inline int32_t *heat_cell(const WrapArrays &w, WrapState &s, int env, int glob_r, int glob_c) {
+    uint32_t *e = w.cm_dir + (size_t)env * CM_DIR_ENTRIES + (glob_r / CM_BLOCK) * CM_BLOCKS_X + (glob_c / CM_BLOCK);
+    uint32_t b = *e;
+    if (!b) {
+        const int i = atomicAdd(&w.ctl[CTL_CM_NEXT], 1);
+        if (i >= w.cm_blocks) {
+            atomicSub(&w.ctl[CTL_CM_NEXT], 1);
+            atomicOr((unsigned int *)&w.ctl[CTL_ERROR], POOL_ERR_HEATMAP);
+            s.overflow = 1;
+            return nullptr;
+        }
+        b = (uint32_t)i + 1;
+        *e = b;
+    }
+    return w.cm_pool + (size_t)(b - 1) * (CM_BLOCK * CM_BLOCK) + (glob_r % CM_BLOCK) * CM_BLOCK + (glob_c % CM_BLOCK);
 }
 
 __device__ __forceinline__ void victory_road_patch(Machine &m) {  // environment.py:1014-1025
@@ -168,9 +210,9 @@ __device__ inline void wrap_mark_render(const WrapArrays &w, WrapState &s, Machi
     int r, c, map_n;
     wrap_position(m, r, c, map_n);
     if (r > 254 || c > 254) return;
-    uint32_t *bm = visited_map(w, s, env, map_n, true);
-    if (!bm) return;
-    uint32_t bit = 1u << (c & 31), *word = bm + r * VIS_ROW_WORDS + (c >> 5);
+    uint32_t *row = visited_row(w, s, env, map_n, r, true);
+    if (!row) return;
+    uint32_t bit = 1u << (c & 31), *word = row + (c >> 5);
     if (at_reset) {
         s.reset_pending = !(*word & bit);
         s.reset_r = r; s.reset_c = c; s.reset_map = map_n;
@@ -208,9 +250,9 @@ __device__ inline double wrap_after_emulation(const WrapArrays &w, WrapState &s,
     int r, c, map_n;
     wrap_position(m, r, c, map_n);
     {  // seen_coords.add((r, c, map_n))  :1344-1345
-        uint32_t *bm = visited_map(w, s, env, map_n, true);
-        if (bm) {
-            uint32_t bit = 1u << (c & 31), *word = bm + r * VIS_ROW_WORDS + (c >> 5);
+        uint32_t *row = visited_row(w, s, env, map_n, r, true);
+        if (row) {
+            uint32_t bit = 1u << (c & 31), *word = row + (c >> 5);
             bool is_reset_tile = s.reset_pending && r == s.reset_r && c == s.reset_c && map_n == s.reset_map;
             if (!(*word & bit) || is_reset_tile) s.n_seen_coords++;
             if (is_reset_tile) s.reset_pending = 0;
@@ -231,29 +273,11 @@ __device__ inline double wrap_after_emulation(const WrapArrays &w, WrapState &s,
     int glob_r = r + c_map_offsets[map_n].y, glob_c = c + c_map_offsets[map_n].x;          // game_map.py:11-18
     if (glob_r < COUNTS_H && glob_c < COUNTS_W) {  // update_heat_map :648-679
         const bool same_map = s.last_map == map_n || s.last_map == -1;
-        const uint32_t cell_id = (uint32_t)(glob_r * COUNTS_W + glob_c);
-        if (w.counts_map) {
-            int32_t *cell = w.counts_map + (size_t)env * COUNTS_H * COUNTS_W + cell_id;
+        int32_t *cell = w.cm_dir ? heat_cell(w, s, env, glob_r, glob_c) : nullptr;
+        if (cell) {
             int32_t old = *cell, neu = same_map ? old + 1 : -1;
             *cell = neu;
             s.coord_sum += (long long)neu - old;
-        } else if (w.cm_hash) {  // big batches: only the cells this env has touched are stored
-            uint2 *tab = w.cm_hash + (size_t)env * w.cm_cap;
-            const uint32_t key = cell_id + 1, mask = (uint32_t)w.cm_cap - 1;
-            uint32_t i = (key * 2654435761u) >> 7 & mask;
-            int probes = 0;
-            for (; probes < w.cm_cap; probes++, i = (i + 1) & mask) {
-                uint2 e = tab[i];
-                if (e.x == key || e.x == 0) {
-                    if (e.x == 0 && s.cm_used >= w.cm_cap - (w.cm_cap >> 3)) { probes = w.cm_cap; break; }  // keep 1/8 free
-                    int32_t old = e.x ? (int32_t)e.y : 0, neu = same_map ? old + 1 : -1;
-                    if (e.x == 0) s.cm_used++;
-                    tab[i] = make_uint2(key, (uint32_t)neu);
-                    s.coord_sum += (long long)neu - old;
-                    break;
-                }
-            }
-            if (probes >= w.cm_cap) s.overflow = 1;  // table full: the cell is not tracked (reported through `faults`)
         }
     }
     s.last_map = map_n;
@@ -387,6 +411,7 @@ __device__ inline double wrap_after_emulation(const WrapArrays &w, WrapState &s,
                 e.x = cx; e.y = cy; e.map = map_id; e.value = val;
             } else {
                 s.overflow = 1;
+                atomicOr((unsigned int *)&w.ctl[CTL_ERROR], POOL_ERR_CUT_COORDS);
             }
             uint32_t tile = (uint32_t)s.cut_state[s.n_cut_state - 1][0] & 0xFF, bit = 1u << (tile & 31);
             if (!(s.cut_tiles_bits[tile >> 5] & bit)) {
@@ -494,9 +519,16 @@ __device__ inline double wrap_after_emulation(const WrapArrays &w, WrapState &s,
 // ------------------------------------------------------------------------------------- kernels
 
 // one thread per env; grid covers the tiles.  info_rows (optional) receives the info scalars of this step.
-__global__ void __launch_bounds__(128) k_wrap_step(DevArrays d, WrapArrays w, double *reward, uint8_t *done, double *info_rows) {
+// `skip` (may be null): envs with skip[e] != 0 do not take this step at all (gbenv_step_masked): reward 0, done 0, state and
+// info row untouched
+__global__ void __launch_bounds__(128) k_wrap_step(DevArrays d, WrapArrays w, double *reward, uint8_t *done, double *info_rows, const uint8_t *skip) {
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, env = tile * GB_TILE + lane;
     if (tile >= d.n_tiles || env >= d.n_envs) return;
+    if (skip && skip[env]) {
+        reward[env] = 0.0;
+        done[env] = 0;
+        return;
+    }
     Machine m;
     machine_load(m, d, tile, lane);
     WrapState &s = w.state[env];
@@ -550,11 +582,7 @@ __global__ void k_wrap_reset_post(DevArrays d, WrapArrays w, const uint8_t *mask
     WrapState &s = w.state[env];
     Machine m;
     machine_load(m, d, env >> 5, env & 31);
-    // zero the visited bitmaps this env used (screen_memory / seen_coords are rebuilt, :1251-1266)
-    uint32_t *vis = w.visited + (size_t)env * w.slots * VIS_MAP_WORDS;
-    for (size_t k = 0; k < (size_t)s.n_slots * VIS_MAP_WORDS; k++) vis[k] = 0;
-    for (int k = 0; k < WRAP_MAPS; k++) s.map_slot[k] = 0xFF;
-    s.n_slots = 0;
+    // screen_memory / seen_coords are rebuilt (:1251-1266): k_vis_release has returned this env's bitmap pages to the pool
     s.reset_count += 1;
     s.time = 0;
     s.max_episode_steps = max_episode_steps;
@@ -592,20 +620,47 @@ __global__ void k_wrap_init(WrapArrays w, int n_envs) {
     s.last_party_size = 1;
     s.reward_scale = 1.0;
     s.max_episode_steps = 20480;
-    for (int k = 0; k < WRAP_MAPS; k++) s.map_slot[k] = 0xFF;
+}
+
+// Reset, first half of the exploration storage: the visited-bitmap pages of every masked env go back to the free stack,
+// zeroed.  One block per env; runs before k_wrap_reset_post (which pops a page for the tile render() marks), so pushes and
+// pops never meet in one launch.
+__global__ void __launch_bounds__(256) k_vis_release(WrapArrays w, const uint8_t *mask, int n_envs) {
+    const int env = blockIdx.x;
+    if (env >= n_envs || (mask && !mask[env])) return;
+    uint32_t *pt = w.vis_pt + (size_t)env * VIS_PT_ENTRIES;
+    for (int k = threadIdx.x; k < VIS_PT_ENTRIES; k += blockDim.x) {
+        const uint32_t pg = pt[k];
+        if (!pg) continue;
+        uint4 *page = (uint4 *)(w.vis_pool + (size_t)(pg - 1) * VIS_PAGE_WORDS);
+        for (int i = 0; i < VIS_PAGE_WORDS / 4; i++) page[i] = make_uint4(0, 0, 0, 0);
+        pt[k] = 0;
+        w.vis_free[atomicAdd(&w.ctl[CTL_VIS_FREE], 1)] = (int32_t)(pg - 1);
+    }
+}
+
+// gbenv_counts_map: one env's heat map as the dense 444 x 436 image; one block per heat-map block
+__global__ void __launch_bounds__(CM_BLOCK * CM_BLOCK) k_cm_gather(WrapArrays w, int env, int32_t *dense) {
+    const int by = blockIdx.x / CM_BLOCKS_X, bx = blockIdx.x % CM_BLOCKS_X, y = by * CM_BLOCK + threadIdx.x / CM_BLOCK, x = bx * CM_BLOCK + threadIdx.x % CM_BLOCK;
+    if (y >= COUNTS_H || x >= COUNTS_W) return;
+    const uint32_t b = w.cm_dir[(size_t)env * CM_DIR_ENTRIES + blockIdx.x];
+    dense[y * COUNTS_W + x] = b ? w.cm_pool[(size_t)(b - 1) * (CM_BLOCK * CM_BLOCK) + threadIdx.x] : 0;
 }
 
 // Observation assembly: block = one 32-env tile, 256 threads.  For each of the 72 output rows the block
 // loads the even framebuffer line (10 words x 32 lanes, coalesced), then writes 32 x 80 RGBA-like pixels
 // as 32-bit words: [grey, grey, grey, visited] (environment.py:266-272, :233-254).
-__global__ void __launch_bounds__(256) k_wrap_obs(DevArrays d, WrapArrays w, const uint8_t *mask, uint8_t *obs, size_t obs_stride) {
+// `mask` (may be null) selects the envs whose rows are written: mask[e] != 0, or mask[e] == 0 when `invert` is set
+__global__ void __launch_bounds__(256) k_wrap_obs(DevArrays d, WrapArrays w, const uint8_t *mask, uint8_t *obs, size_t obs_stride, int invert = 0) {
     __shared__ uint32_t s_fb[FB_LINE_WORDS][32];
     __shared__ uint32_t s_win[32][3];  // 80-bit visited window of the current row, per env
-    __shared__ int s_r[32], s_c[32], s_map_slot[32];
+    __shared__ int s_r[32], s_c[32];
+    __shared__ uint32_t s_page[32][VIS_BANDS];  // the current map's bitmap pages (index + 1, 0 = none)
     const int tile = blockIdx.x, tid = threadIdx.x;
     if (tid < 32) {
         int env = tile * 32 + tid;
-        int r = 0, c = 0, slot = -1;
+        int r = 0, c = 0;
+        for (int b = 0; b < VIS_BANDS; b++) s_page[tid][b] = 0;
         if (env < d.n_envs) {
             const uint8_t *memb = (const uint8_t *)(d.mem + il_index(tile, MEM_WORDS, 0, tid));
             auto rd = [&](uint32_t a) { uint32_t i = MEM_WRAM + (a - 0xC000); return (int)memb[((i >> 2) << 7) | (i & 3)]; };
@@ -613,10 +668,9 @@ __global__ void __launch_bounds__(256) k_wrap_obs(DevArrays d, WrapArrays w, con
             c = rd(0xD362);
             int map_n = rd(0xD35E);
             map_n = map_n > 247 ? 247 : map_n;
-            int sl = w.state[env].map_slot[map_n];
-            slot = sl == 0xFF ? -1 : sl;
+            for (int b = 0; b < VIS_BANDS; b++) s_page[tid][b] = w.vis_pt[(size_t)env * VIS_PT_ENTRIES + map_n * VIS_BANDS + b];
         }
-        s_r[tid] = r; s_c[tid] = c; s_map_slot[tid] = slot;
+        s_r[tid] = r; s_c[tid] = c;
     }
     __syncthreads();
     const uint32_t grey_lut = 0x00559900u | 0xFFu;  // shade 0..3 -> 0xFF 0x99 0x55 0x00 (byte k of the word)
@@ -629,8 +683,9 @@ __global__ void __launch_bounds__(256) k_wrap_obs(DevArrays d, WrapArrays w, con
             int e = tid / 3, part = tid % 3, env = tile * 32 + e;
             uint32_t bits = 0;
             int rr = s_r[e] - 36 + i;
-            if (env < d.n_envs && s_map_slot[e] >= 0 && rr >= 0 && rr < 255) {
-                const uint32_t *row = w.visited + ((size_t)env * w.slots + s_map_slot[e]) * VIS_MAP_WORDS + rr * VIS_ROW_WORDS;
+            const uint32_t pg = (env < d.n_envs && rr >= 0 && rr < 255) ? s_page[e][rr / VIS_BAND_ROWS] : 0;
+            if (pg) {
+                const uint32_t *row = w.vis_pool + (size_t)(pg - 1) * VIS_PAGE_WORDS + (rr % VIS_BAND_ROWS) * VIS_ROW_WORDS;
                 int c0 = s_c[e] - 40 + part * 32;  // first column of this 32-bit part
                 for (int b = 0; b < 32; b++) {
                     int cc = c0 + b;
@@ -642,7 +697,7 @@ __global__ void __launch_bounds__(256) k_wrap_obs(DevArrays d, WrapArrays w, con
         __syncthreads();
         for (int k = tid; k < 32 * 80; k += 256) {
             int e = k / 80, j = k % 80, env = tile * 32 + e;
-            if (env < d.n_envs && (!mask || mask[env])) {
+            if (env < d.n_envs && (!mask || (mask[env] != 0) != (invert != 0))) {
                 uint32_t shade = (s_fb[j >> 3][e] >> (4 * (j & 7))) & 3;  // pixel x = 2j
                 uint32_t g = (grey_lut >> (8 * shade)) & 0xFF;
                 uint32_t vis = (s_win[e][j >> 5] >> (j & 31)) & 1 ? 0xFFu : 0u;

@@ -57,6 +57,8 @@ struct gbenv {
     unsigned long long launches = 0;
     int lanes = 32;  // envs per warp in k_run_frames
     size_t smem_opted = 48 * 1024;
+    int32_t *pool_err_host = nullptr;  // pinned copy of WrapArrays.ctl[CTL_ERROR], refreshed asynchronously after every step / reset
+    int32_t *d_cm_dense = nullptr;     // staging for gbenv_counts_map
     std::string err;
 };
 
@@ -95,6 +97,28 @@ static cudaStream_t use_stream(gbenv *h, cudaStream_t s) {
 static cudaStream_t pick(gbenv *h, void *stream) { return use_stream(h, (cudaStream_t)stream); }
 static cudaStream_t own(gbenv *h) { return use_stream(h, h->stream); }
 
+// all bitmap pages start on the free stack
+__global__ void k_pool_init(WrapArrays w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.vis_pages) w.vis_free[i] = i;
+    if (i == 0) { w.ctl[CTL_VIS_FREE] = w.vis_pages; w.ctl[CTL_CM_NEXT] = 0; w.ctl[CTL_ERROR] = 0; }
+}
+
+// A pool of the exploration storage ran dry in an earlier step: the bits are sticky and the handle refuses further work.
+static int pool_error(gbenv *h) {
+    const int32_t e = h->pool_err_host ? *(volatile int32_t *)h->pool_err_host : 0;
+    if (!e) return GBENV_OK;
+    std::string msg = "exploration storage exhausted:";
+    if (e & POOL_ERR_VISITED) msg += " visited-bitmap page pool (GBENV_VISITED_PAGES)";
+    if (e & POOL_ERR_HEATMAP) msg += " heat-map block pool (GBENV_COUNTS_BLOCKS)";
+    if (e & POOL_ERR_CUT_COORDS) msg += " cut_coords table (64 distinct tiles per episode)";
+    msg += "; rewards / observations of the affected envs no longer match the reference";
+    return fail(h, GBENV_E_NOMEM, msg.c_str());
+}
+static void queue_pool_error_copy(gbenv *h, cudaStream_t st) {
+    cudaMemcpyAsync(h->pool_err_host, h->w.ctl + CTL_ERROR, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+}
+
 // ------------------------------------------------------------------------------- lifetime
 
 extern "C" int gbenv_abi_version(void) { return GBENV_ABI_VERSION; }
@@ -128,7 +152,10 @@ extern "C" int gbenv_destroy(gbenv *h) {
     cudaDeviceSynchronize();
     for (auto &t : h->templates) cudaFree(t.d_image);
     cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree((void *)h->d.rom); cudaFree((void *)h->d.rom_dec);
-    cudaFree(h->w.state); cudaFree(h->w.visited); cudaFree(h->w.counts_map); cudaFree(h->w.cm_hash);
+    cudaFree(h->w.state); cudaFree(h->w.vis_pt); cudaFree(h->w.vis_pool); cudaFree(h->w.vis_free); cudaFree(h->w.cm_dir); cudaFree(h->w.cm_pool);
+    cudaFree(h->w.ctl);
+    if (h->pool_err_host) cudaFreeHost(h->pool_err_host);
+    cudaFree(h->d_cm_dense);
     cudaFree(h->d_counters); cudaFree(h->d_stage_image); cudaFree(h->d_stage_buf); cudaFree(h->d_info_rows);
     cudaFree(h->d_env_ids); cudaFree(h->d_mask); cudaFree(h->d_init_tmpl); cudaFree(h->d_tmpl_images); cudaFree(h->d_tmpl_versions);
     for (int k = 0; k < 2; k++) {
@@ -198,17 +225,6 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
     h->d.rom_banks = (uint32_t)(rom_len / 0x4000);
     h->d.n_envs = n_envs;
     h->d.n_tiles = h->n_tiles;
-    // visited-bitmap slots per env: all 248 maps when that fits an 8 GiB budget, otherwise fewer
-    // (an env that visits more maps than it has slots raises the `faults` counter; GBENV_VISITED_SLOTS overrides)
-    int slots = WRAP_MAPS;
-    size_t budget = (size_t)8 << 30, per_slot = (size_t)VIS_MAP_WORDS * 4;
-    if ((size_t)n_envs * slots * per_slot > budget) slots = (int)(budget / ((size_t)n_envs * per_slot));
-    if (slots < 8) slots = 8;
-    if (const char *ev = getenv("GBENV_VISITED_SLOTS")) {
-        int v = atoi(ev);
-        if (v >= 1 && v <= WRAP_MAPS) slots = v;
-    }
-    h->w.slots = slots;
     {   // envs per warp: the interpreter is latency-bound, so spread the batch over as many warps as are resident
         // at once (one wave: SMs x STEP_MIN_BLOCKS blocks) and no more; GBENV_LANES / gbenv_set_lanes_per_warp override.
         int sms = 148;
@@ -225,24 +241,34 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
         h->lanes = lanes;
     }
     ALLOC(h->w.state, sizeof(WrapState) * (size_t)n_envs);
-    ALLOC(h->w.visited, (size_t)n_envs * slots * per_slot);
-    {   // heat maps (environment.py:648-679): dense 444x436 int32 per env while they fit in 4 GiB, else a per-env hash of the
-        // cells actually touched (one new cell per step at most), sized to a 2 GiB budget; GBENV_COUNTS_MAP=dense|sparse|0
-        bool dense = (size_t)n_envs * COUNTS_H * COUNTS_W * 4 <= ((size_t)4 << 30), sparse = !dense;
-        if (const char *ev = getenv("GBENV_COUNTS_MAP")) {
-            dense = !strcmp(ev, "dense") || !strcmp(ev, "1");
-            sparse = !strcmp(ev, "sparse");
+    {   // exploration storage (gb_wrap.cuh): page tables / directories per env, pages and blocks from shared pools.  A pool
+        // holds everything the batch could ever use when that fits its budget (8 GiB of 2 KiB bitmap pages, 4 GiB of 1 KiB
+        // heat-map blocks), otherwise the budget: e.g. 32,768 envs share 4.2 M bitmap pages -- 128 per env on average, all
+        // 992 for any one of them.  GBENV_VISITED_PAGES / GBENV_COUNTS_BLOCKS override the pool sizes (tests);
+        // GBENV_COUNTS_MAP=0 switches the heat maps off.
+        size_t pages = (size_t)n_envs * VIS_PT_ENTRIES, max_pages = ((size_t)8 << 30) / (VIS_PAGE_WORDS * 4);
+        if (pages > max_pages) pages = max_pages;
+        if (const char *ev = getenv("GBENV_VISITED_PAGES")) {
+            long v = atol(ev);
+            if (v >= 1 && (size_t)v <= max_pages) pages = (size_t)v;
         }
-        if (dense) ALLOC(h->w.counts_map, (size_t)n_envs * COUNTS_H * COUNTS_W * sizeof(int32_t));
-        if (sparse) {
-            int cap = 65536;
-            while (cap > 1024 && (size_t)n_envs * cap * sizeof(uint2) > ((size_t)2 << 30)) cap >>= 1;
-            if (const char *ev = getenv("GBENV_COUNTS_SLOTS")) {
-                int v = atoi(ev);
-                if (v >= 16 && v <= (1 << 18) && (v & (v - 1)) == 0) cap = v;
+        h->w.vis_pages = (int)pages;
+        ALLOC(h->w.vis_pt, (size_t)n_envs * VIS_PT_ENTRIES * sizeof(uint32_t));
+        ALLOC(h->w.vis_pool, pages * VIS_PAGE_WORDS * sizeof(uint32_t));
+        ALLOC(h->w.vis_free, pages * sizeof(int32_t));
+        ALLOC(h->w.ctl, 8 * sizeof(int32_t));
+        bool heat = true;
+        if (const char *ev = getenv("GBENV_COUNTS_MAP")) heat = strcmp(ev, "0") != 0;
+        if (heat) {
+            size_t blocks = (size_t)n_envs * CM_DIR_ENTRIES, max_blocks = ((size_t)4 << 30) / (CM_BLOCK * CM_BLOCK * 4);
+            if (blocks > max_blocks) blocks = max_blocks;
+            if (const char *ev = getenv("GBENV_COUNTS_BLOCKS")) {
+                long v = atol(ev);
+                if (v >= 1 && (size_t)v <= max_blocks) blocks = (size_t)v;
             }
-            h->w.cm_cap = cap;
-            ALLOC(h->w.cm_hash, (size_t)n_envs * cap * sizeof(uint2));
+            h->w.cm_blocks = (int)blocks;
+            ALLOC(h->w.cm_dir, (size_t)n_envs * CM_DIR_ENTRIES * sizeof(uint32_t));
+            ALLOC(h->w.cm_pool, blocks * CM_BLOCK * CM_BLOCK * sizeof(int32_t));
         }
     }
     ALLOC(h->d_counters, 8 * sizeof(unsigned long long));
@@ -274,7 +300,10 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
         CK(cudaGetLastError());
     }
     k_wrap_init<<<(n_envs + 127) / 128, 128, 0, h->stream>>>(h->w, n_envs);
+    k_pool_init<<<(h->w.vis_pages + 255) / 256, 256, 0, h->stream>>>(h->w);
     CK(cudaGetLastError());
+    CK(cudaHostAlloc((void **)&h->pool_err_host, sizeof(int32_t), cudaHostAllocDefault));
+    *h->pool_err_host = 0;
     std::vector<uint32_t> img;
     power_on_image(img);
     CK(cudaMemcpyAsync(h->d_stage_image, img.data(), IMG_WORDS * 4, cudaMemcpyHostToDevice, h->stream));
@@ -368,10 +397,11 @@ extern "C" int gbenv_save_state(gbenv *h, int env, uint8_t *blob) {
 
 // ------------------------------------------------------------------------------- emulator
 
-static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int render_mode, cudaStream_t st) {
+static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int render_mode, cudaStream_t st, const uint8_t *skip_dev = nullptr) {
     RunParams p;
     p.d = h->d;
     p.actions = actions_dev;
+    p.skip = skip_dev;
     p.n_frames = n_frames;
     p.render_mode = render_mode;
     p.release_frame = 8;
@@ -490,7 +520,9 @@ extern "C" int gbenv_reset_dev(gbenv *h, const uint8_t *mask_dev, int max_episod
     if (!h || !obs_dev || obs_stride < GBENV_OBS_BYTES || (obs_stride & 3)) return fail(h, GBENV_E_ARG, "gbenv_reset: bad argument");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = pick(h, stream);
-    int rc = upload_template_tables(h, st);
+    int rc = pool_error(h);
+    if (rc) return rc;
+    rc = upload_template_tables(h, st);
     if (rc) return rc;
     int blocks = (h->n + 127) / 128;
     k_wrap_reset_pre<<<blocks, 128, 0, st>>>(h->d, h->w, mask_dev);  // environment.py:1239: D778 |= 0x10 before the load
@@ -501,10 +533,12 @@ extern "C" int gbenv_reset_dev(gbenv *h, const uint8_t *mask_dev, int max_episod
         h->launches++;
         if (!mask_dev) h->loads_pending = false;  // every env has had its first reset now
     }
+    k_vis_release<<<h->n, 256, 0, st>>>(h->w, mask_dev, h->n);  // the envs' bitmap pages go back to the pool
     k_wrap_reset_post<<<blocks, 128, 0, st>>>(h->d, h->w, mask_dev, max_episode_steps, reward_scale);
     k_wrap_obs<<<h->n_tiles, 256, 0, st>>>(h->d, h->w, mask_dev, obs_dev, obs_stride);
-    h->launches += 2;
+    h->launches += 3;
     CK(cudaGetLastError());
+    queue_pool_error_copy(h, st);
     return GBENV_OK;
 }
 
@@ -538,9 +572,20 @@ static int fold_events(gbenv *h, unsigned long long upto) {
 
 extern "C" int gbenv_step(gbenv *h, const uint8_t *actions_dev, uint8_t *obs_dev, size_t obs_stride, double *reward_dev, uint8_t *done_dev,
                           void *stream) {
+    return gbenv_step_masked(h, actions_dev, nullptr, obs_dev, obs_stride, reward_dev, done_dev, stream);
+}
+
+// Environment.step for the envs with skip_dev[e] == 0 (null: all).  A skipped env is not emulated, its wrapper state, info row
+// and observation row stay as they are, and it reports reward 0 / done 0.
+extern "C" int gbenv_step_masked(gbenv *h, const uint8_t *actions_dev, const uint8_t *skip_dev, uint8_t *obs_dev, size_t obs_stride, double *reward_dev,
+                                 uint8_t *done_dev, void *stream) {
     if (!h || !actions_dev || !obs_dev || !reward_dev || !done_dev || obs_stride < GBENV_OBS_BYTES || (obs_stride & 3))
         return fail(h, GBENV_E_ARG, "gbenv_step: bad argument");
     CK(cudaSetDevice(h->device));
+    {
+        int rce = pool_error(h);
+        if (rce) return rce;
+    }
     cudaStream_t st = pick(h, stream);
     if (h->ev_step - h->ev_folded >= (unsigned long long)gbenv::EV_RING) {  // slot about to be reused: fold it first
         int rcf = fold_events(h, h->ev_folded + 1);
@@ -548,15 +593,16 @@ extern "C" int gbenv_step(gbenv *h, const uint8_t *actions_dev, uint8_t *obs_dev
     }
     cudaEvent_t *ev = h->ev[h->ev_step % gbenv::EV_RING];
     CK(cudaEventRecord(ev[0], st));
-    int rc = launch_run(h, actions_dev, GBENV_ACT_FREQ, 2, st);
+    int rc = launch_run(h, actions_dev, GBENV_ACT_FREQ, 2, st, skip_dev);
     if (rc) return rc;
     CK(cudaEventRecord(ev[1], st));
     int blocks = (h->n_tiles * GB_TILE + 127) / 128;
-    k_wrap_step<<<blocks, 128, 0, st>>>(h->d, h->w, reward_dev, done_dev, h->d_info_rows);
-    k_wrap_obs<<<h->n_tiles, 256, 0, st>>>(h->d, h->w, nullptr, obs_dev, obs_stride);
+    k_wrap_step<<<blocks, 128, 0, st>>>(h->d, h->w, reward_dev, done_dev, h->d_info_rows, skip_dev);
+    k_wrap_obs<<<h->n_tiles, 256, 0, st>>>(h->d, h->w, skip_dev, obs_dev, obs_stride, 1);
     h->launches += 2;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev[2], st));
+    queue_pool_error_copy(h, st);
     h->ev_step++;
     h->ev_valid = true;
     return GBENV_OK;
@@ -657,20 +703,24 @@ extern "C" int gbenv_reduce_info(gbenv *h, double *sum_dev, void *stream) {
 
 extern "C" int gbenv_counts_map(gbenv *h, int env, int32_t *map_host) {
     if (!h || env < 0 || env >= h->n || !map_host) return fail(h, GBENV_E_ARG, "gbenv_counts_map: bad argument");
-    if (!h->w.counts_map && !h->w.cm_hash) return fail(h, GBENV_E_ARG, "gbenv_counts_map: exploration map tracking is disabled (GBENV_COUNTS_MAP=0)");
+    if (!h->w.cm_dir) return fail(h, GBENV_E_ARG, "gbenv_counts_map: exploration map tracking is disabled (GBENV_COUNTS_MAP=0)");
     CK(cudaSetDevice(h->device));
-    own(h);  // ordered after whatever was last queued on this handle, on any stream
-    CK(cudaStreamSynchronize(h->stream));
-    if (!h->w.counts_map) {  // sparse: rebuild the dense image from this env's hash entries
-        std::vector<uint2> tab((size_t)h->w.cm_cap);
-        CK(cudaMemcpy(tab.data(), h->w.cm_hash + (size_t)env * h->w.cm_cap, tab.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
-        memset(map_host, 0, (size_t)COUNTS_H * COUNTS_W * 4);
-        for (const uint2 &e : tab)
-            if (e.x) map_host[e.x - 1] = (int32_t)e.y;
-        return GBENV_OK;
-    }
-    CK(cudaMemcpy(map_host, h->w.counts_map + (size_t)env * COUNTS_H * COUNTS_W, (size_t)COUNTS_H * COUNTS_W * 4, cudaMemcpyDeviceToHost));
+    cudaStream_t st = own(h);  // ordered after whatever was last queued on this handle, on any stream
+    if (!h->d_cm_dense) CK(cudaMalloc((void **)&h->d_cm_dense, (size_t)COUNTS_H * COUNTS_W * sizeof(int32_t)));
+    k_cm_gather<<<CM_DIR_ENTRIES, CM_BLOCK * CM_BLOCK, 0, st>>>(h->w, env, h->d_cm_dense);  // the env's blocks -> dense 444 x 436
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(map_host, h->d_cm_dense, (size_t)COUNTS_H * COUNTS_W * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return GBENV_OK;
+}
+
+// Blocks until everything queued on the handle is done; GBENV_E_NOMEM when a pool of the exploration storage ran dry.
+extern "C" int gbenv_check(gbenv *h) {
+    if (!h) return GBENV_E_ARG;
+    int rc = gbenv_sync(h);
+    if (rc) return rc;
+    return pool_error(h);
 }
 
 // ------------------------------------------------------------------------------- diagnostics

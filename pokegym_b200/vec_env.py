@@ -175,8 +175,10 @@ class VecEnvironment:
                               obs_stride=_capi.OBS_BYTES, stream=self._stream())
         return obs.view(self.num_envs, *OBS_SHAPE), {}
 
-    def step(self, actions):
-        """Environment.step for every env.  `actions`: uint8/int tensor [N] on the device (or array-like)."""
+    def step(self, actions, skip=None):
+        """Environment.step for every env.  `actions`: uint8/int tensor [N] on the device (or array-like).
+        `skip` (uint8 device tensor [N], optional): envs with skip[e] != 0 sit this step out -- reward 0, done False, their
+        observation row keeps what it holds (e.g. the reset observation just written by reset(mask=...))."""
         torch = self.torch
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), device=self.device)
@@ -188,7 +190,15 @@ class VecEnvironment:
             raise IndexError("action out of range 0..7")
         self._t += 1
         obs = self._obs_target()
-        self.handle.step(actions, obs, self._reward, self._done, obs_stride=_capi.OBS_BYTES, stream=self._stream())
+        if skip is None:
+            self.handle.step(actions, obs, self._reward, self._done, obs_stride=_capi.OBS_BYTES, stream=self._stream())
+        else:
+            if skip.dtype != torch.uint8 or skip.device != self.device or not skip.is_contiguous() or skip.numel() != self.num_envs:
+                raise ValueError(f"skip must be a contiguous uint8 tensor with {self.num_envs} entries on {self.device}")
+            if self.rollout is not None:  # a new rollout slot: the rows of the envs that sit out must carry over
+                prev = self.rollout[(self._t - 1) % self.rollout.shape[0]]
+                obs.view(self.num_envs, -1)[skip.bool()] = prev.view(self.num_envs, -1)[skip.bool()]
+            self.handle.step_masked(actions, skip, obs, self._reward, self._done, obs_stride=_capi.OBS_BYTES, stream=self._stream())
         done = self._done.bool()
         if self.auto_reset:
             # envs that just finished are reset on the device, masked by the done vector the step wrote: their row of `obs`

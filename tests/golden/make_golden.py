@@ -56,7 +56,7 @@ def wrapper_golden(name, rom_name, start_blob, n_steps, seed, max_episode_steps,
     print(name, "steps", n_steps, "info dicts", len(info_steps), "sum|reward|", float(np.abs(ref["rewards"]).sum()), "nonzero rewards", int(np.count_nonzero(ref["rewards"])))
 
 
-def ppu_golden(n_pick=16):
+def ppu_golden(n_pick=264):  # every v9 fixture the reference ships
     files = sorted(p for p in REF.rglob("*") if p.is_file() and p.stat().st_size == 142_610)
     # spread over the fixture directories; prefer states with a visible window / many sprites
     pick = [files[i] for i in np.linspace(0, len(files) - 1, n_pick).astype(int)]
@@ -73,6 +73,35 @@ def ppu_golden(n_pick=16):
         recs["names"].append(str(p.relative_to(REF)))
     np.savez_compressed(OUT / "ppu_kat.npz", **{k: np.array(v) for k, v in recs.items()})
     print("ppu_kat:", len(pick), "fixtures")
+
+
+def wrapper_sweep_golden(oracle_lib, n_steps=6):
+    """3. ref_wrapper_sweep.npz -- ALL 264 v9 save-states the reference ships, each reset + stepped `n_steps` times by the
+    unmodified reference wrapper (on the PyBoy shim over the oracle core, synthetic ROM): reward, done, observation CRC and
+    state hash per step.  The states cover every outcome of Game.process_game_states (red_ram_api.py:59-73, :149-225,
+    :542-602), wild / trainer battles, menus and overworld; one batch of 264 envs replays them through CUDA."""
+    import ref_shim
+
+    rom = synth_rom.build_pokelike_rom()
+    files = sorted(p for p in REF.rglob("*") if p.is_file() and p.stat().st_size == 142_610)
+    rng = np.random.default_rng(264)
+    actions = rng.integers(0, 8, (len(files), n_steps)).astype(np.uint8)
+    rec = dict(states=[], names=[], rewards=[], dones=[], obs_crc=[], reset_obs_crc=[], state_sha=[])
+    for k, p in enumerate(files):
+        blob = p.read_bytes()
+        ref = ref_shim.run_reference_episode(rom, oracle_lib, blob, actions[k], max_episode_steps=4)  # done fires at step 4
+        rec["states"].append(np.frombuffer(blob, dtype=np.uint8))
+        rec["names"].append(str(p.relative_to(REF)))
+        rec["rewards"].append(ref["rewards"])
+        rec["dones"].append(ref["dones"])
+        rec["obs_crc"].append([zlib.crc32(o.tobytes()) for o in ref["obs"]])
+        rec["reset_obs_crc"].append(zlib.crc32(ref["reset_obs"][0].tobytes()))
+        rec["state_sha"].append(np.frombuffer(hashlib.sha256(ref["states"][-1]).digest(), dtype=np.uint8))
+    np.savez_compressed(OUT / "ref_wrapper_sweep.npz", states=np.stack(rec["states"]), names=np.array(rec["names"]), actions=actions,
+                        rewards=np.array(rec["rewards"], dtype=np.float64), dones=np.array(rec["dones"], dtype=np.uint8),
+                        obs_crc=np.array(rec["obs_crc"], dtype=np.uint32), reset_obs_crc=np.array(rec["reset_obs_crc"], dtype=np.uint32),
+                        state_sha=np.stack(rec["state_sha"]), max_episode_steps=4)
+    print("ref_wrapper_sweep:", len(files), "states x", n_steps, "steps; distinct rewards", len(set(np.array(rec["rewards"]).ravel().tolist())))
 
 
 def main():
@@ -93,6 +122,7 @@ def main():
             p = cands[len(cands) // 2]
         wrapper_golden(name, "pokelike", p.read_bytes(), 60, 7, 40, (45,), lib)
     ppu_golden()
+    wrapper_sweep_golden(lib)
 
 
 if __name__ == "__main__":

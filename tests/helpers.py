@@ -66,6 +66,32 @@ def replay_wrapper_golden(handle, gold, xp=None, to_dev=lambda a: a, to_host=lam
     assert np.array_equal(to_host(obs).reshape(72, 80, 4), gold["last_obs"])
 
 
+def replay_wrapper_sweep(handle, gold, to_dev=lambda a: a, to_host=lambda a: a):
+    """ref_wrapper_sweep.npz (all 264 reference save-states x 6 steps of the unmodified reference wrapper) replayed as ONE
+    batch: env i starts from state i.  `handle` has 264 envs."""
+    n = len(gold["names"])
+    for i in range(n):
+        handle.set_initial_template(handle.add_state_template(gold["states"][i].tobytes()), np.array([i], dtype=np.int32))
+    obs = to_dev(np.zeros((n, _capi.OBS_BYTES), dtype=np.uint8))
+    rew = to_dev(np.zeros(n, dtype=np.float64))
+    done = to_dev(np.zeros(n, dtype=np.uint8))
+    handle.reset(obs, max_episode_steps=int(gold["max_episode_steps"]))
+    o = to_host(obs)
+    for i in range(n):
+        assert zlib.crc32(o[i].tobytes()) == int(gold["reset_obs_crc"][i]), f"{gold['names'][i]}: reset observation differs from the reference"
+    for t in range(gold["actions"].shape[1]):
+        handle.step(to_dev(np.ascontiguousarray(gold["actions"][:, t])), obs, rew, done)
+        r, d, o = to_host(rew), to_host(done), to_host(obs)
+        bad = np.nonzero(r != gold["rewards"][:, t])[0]
+        assert bad.size == 0, f"step {t}: reward differs from the reference for {[str(gold['names'][i]) for i in bad[:5]]}"
+        assert np.array_equal(d, gold["dones"][:, t]), f"step {t}: done differs"
+        for i in range(n):
+            assert zlib.crc32(o[i].tobytes()) == int(gold["obs_crc"][i, t]), f"step {t}: {gold['names'][i]}: observation differs from the reference"
+    for i in range(n):
+        sha = np.frombuffer(hashlib.sha256(handle.save_state(i)).digest(), dtype=np.uint8)
+        assert np.array_equal(sha, gold["state_sha"][i]), f"{gold['names'][i]}: emulator state differs after the replay"
+
+
 def ppu_kat_blob(base_blob: bytes, kat, i: int) -> bytes:
     st = parse_state(base_blob)
     st.raw["vram"] = kat["vram"][i]

@@ -14,6 +14,17 @@ static void gb_trace(uint32_t pc, uint32_t bcde, uint32_t hlaf, uint32_t sp, uin
 }
 extern "C" void hs_trace(const char *path) { if (g_trace) fclose(g_trace); g_trace = path ? fopen(path, "w") : nullptr; }
 #endif
+#if defined(GB_SLOT_TRACE)
+// convergence study (tools/trace_convergence.py): every executed instruction of every env as one 64-bit record
+#include <vector>
+static std::vector<unsigned long long> g_slots;
+#define GB_TRACE_SLOT(kind, phys, dx, dw) g_slots.push_back(((unsigned long long)(kind) << 48) | ((unsigned long long)((dw) & 0xFFFFu) << 32) | (((dx) & 0xFFull) << 24) | ((phys) & 0xFFFFFFull))
+extern "C" size_t hs_slots(unsigned long long *out, size_t cap) {
+    size_t n = g_slots.size();
+    if (out) { memcpy(out, g_slots.data(), sizeof(unsigned long long) * (n < cap ? n : cap)); g_slots.clear(); }
+    return n;
+}
+#endif
 #include "../../pokegym_b200/csrc/gb_image.h"
 #include "../../pokegym_b200/csrc/gb_kernels.cuh"
 
@@ -87,12 +98,13 @@ int hs_save_blob(void *p, int env, uint8_t *out) {
 int hs_run(void *p, const uint8_t *actions, int n_frames, int render_mode) {
     HostSim *h = (HostSim *)p;
     RunParams rp;
-    rp.d = h->d; rp.actions = actions; rp.n_frames = n_frames; rp.render_mode = render_mode; rp.release_frame = 8; rp.lanes = 1;
+    rp.d = h->d; rp.actions = actions; rp.skip = nullptr; rp.n_frames = n_frames; rp.render_mode = render_mode; rp.release_frame = 8; rp.lanes = 1;
     rp.bank_mask = (h->d.rom_banks & (h->d.rom_banks - 1)) == 0 ? h->d.rom_banks - 1 : 0;
     rp.counters = h->counters;
     for (int env = 0; env < h->n; env++) {
         EnvSlot slot;
         uint32_t line[FB_LINE_WORDS], keys[10];
+        GB_TRACE_SLOT(3, 0, 0, 0);  // a new env's records start here
         machine_load(slot.m, rp.d, env >> 5, env & 31);
         const int button = actions ? c_action_button[actions[env] & 7] : -1;
         slot.m.rline = line; slot.m.rkeys = keys; slot.m.rls = 1;

@@ -91,6 +91,51 @@ def test_step_reward_obs_match_oracle(cuda_lib, oracle_lib, roms):
     assert np.array_equal(gpu.counts_map(3), cpu.counts_map(3))
 
 
+@pytest.mark.parametrize("lanes", [1, 8, 32])
+def test_config5_mixed_reference_states_divergence_stress(cuda_lib, oracle_lib, roms, lanes):
+    """BASELINE.json config 5: env i is reset from reference save-state i mod 40 (tests/golden/red_states_mixed.npz: overworld,
+    wild and trainer battles, menus, text boxes, ROM banks 1-38, HALTed and mid-instruction PCs, picked by
+    tools/select_mixed_states.py), so neighbouring lanes of a warp run unrelated code from step one.  200 random-action steps,
+    every step: reward / done / observation equal to the oracle; full emulator state of every env every 50 steps.  Illegal
+    opcodes are expected (the states' PCs land in the synthetic ROM's data) and must match too."""
+    import torch
+    from helpers import GOLDEN
+
+    blobs = [b.tobytes() for b in np.load(GOLDEN / "red_states_mixed.npz")["states"]]
+    n, steps = 160, 200
+    gpu, cpu = _pair(cuda_lib, oracle_lib, roms("pokelike"), n)
+    gpu.set_lanes_per_warp(lanes)
+    for k, blob in enumerate(blobs):
+        ids = np.arange(k, n, len(blobs), dtype=np.int32)
+        for h in (gpu, cpu):
+            h.set_initial_template(h.add_state_template(blob), ids)
+    og = torch.zeros((n, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
+    rg = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dg = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    oc, rc, dc = np.zeros((n, _capi.OBS_BYTES), np.uint8), np.zeros(n), np.zeros(n, np.uint8)
+    gpu.reset(og, max_episode_steps=120)
+    cpu.reset(oc, max_episode_steps=120)
+    assert np.array_equal(og.cpu().numpy(), oc)
+    _assert_same_states(gpu, cpu, range(n), "after the first reset")
+    rng = np.random.default_rng(55)
+    for s in range(steps):
+        act = rng.integers(0, 8, n).astype(np.uint8)
+        gpu.step(torch.from_numpy(act).cuda(), og, rg, dg)
+        cpu.step(act, oc, rc, dc)
+        assert np.array_equal(rg.cpu().numpy(), rc), f"reward differs at step {s}"
+        assert np.array_equal(dg.cpu().numpy(), dc), f"done differs at step {s}"
+        assert np.array_equal(og.cpu().numpy(), oc), f"obs differs at step {s}"
+        if s == 119:  # episode end: device-side auto-reset of the finished envs (no state reload after the first reset)
+            assert dc.all()
+            gpu.reset_dev(og, mask_dev=dg, max_episode_steps=120)
+            cpu.reset(oc, mask=dc, max_episode_steps=120)
+            assert np.array_equal(og.cpu().numpy(), oc)
+        if s % 50 == 49 or s == steps - 1:
+            _assert_same_states(gpu, cpu, range(n), f"mixed states step {s}")
+    cg, cc = gpu.counters(), cpu.counters()
+    assert cg.instructions == cc.instructions and cg.cycles == cc.cycles and cg.faults == cc.faults
+
+
 def test_step_host_entry_point(cuda_lib, oracle_lib, roms):
     n = 40
     gpu, cpu = _pair(cuda_lib, oracle_lib, roms("pokelike"), n)
@@ -220,20 +265,22 @@ def test_full_size_batch_matches_replicated_small_batch(cuda_lib, oracle_lib, ro
     assert gpu.counters().faults == 0
 
 
-def test_sparse_heat_map_matches_dense(cuda_lib, oracle_lib, roms, monkeypatch):
-    """GBENV_COUNTS_MAP=sparse (the representation big batches get) against the oracle's dense map, including the
-    overflow report when the per-env table is made too small."""
+def test_paged_exploration_storage_many_maps(cuda_lib, oracle_lib, roms, monkeypatch):
+    """Visited bitmaps and heat maps are paged out of shared pools (gb_wrap.cuh): envs that walk through 40+ maps, far more
+    than an equal share of a small pool would allow, still match the oracle's observation (channel 3 = visited window,
+    environment.py:256-274), reward (exploration term, :1344-1345, :1375), info rows and heat maps; pages return to the pool
+    on reset.  A heat-map pool that runs dry is reported as an error."""
     import torch
 
-    n, steps = 40, 30
+    n, steps = 48, 56
     rom = roms("pokelike")
-    monkeypatch.setenv("GBENV_COUNTS_MAP", "sparse")
-    monkeypatch.setenv("GBENV_COUNTS_SLOTS", "64")
+    monkeypatch.setenv("GBENV_VISITED_PAGES", "400")  # 48 envs x 992 entries would be 47,616: 400 is < 9 pages per env
     gpu = _capi.Handle(cuda_lib, n, rom, 0)
-    monkeypatch.setenv("GBENV_COUNTS_SLOTS", "16")
+    monkeypatch.setenv("GBENV_COUNTS_BLOCKS", "50")
     tiny = _capi.Handle(cuda_lib, n, rom, 0)
     cpu = _capi.Handle(oracle_lib, n, rom)
     og = torch.zeros((n, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
+    ot = torch.zeros_like(og)
     rg = torch.zeros(n, dtype=torch.float64, device="cuda")
     dg = torch.zeros(n, dtype=torch.uint8, device="cuda")
     oc, rc, dc = np.zeros((n, _capi.OBS_BYTES), np.uint8), np.zeros(n), np.zeros(n, np.uint8)
@@ -243,22 +290,41 @@ def test_sparse_heat_map_matches_dense(cuda_lib, oracle_lib, roms, monkeypatch):
     cpu.tick(40, True)
     cpu.reset(oc)
     rng = np.random.default_rng(3)
+    walkers = (1, 17, 40)  # these envs are teleported through a new map (and rows in all four 64-row bands) every step
+    tiny_failed = False
     for s in range(steps):
+        if s == 30:  # episode boundary for half of the envs: their pages go back to the pool and are handed out again
+            mask = (np.arange(n) % 2 == 1).astype(np.uint8)
+            gpu.reset(og, mask=mask)
+            cpu.reset(oc, mask=mask)
+            assert np.array_equal(og.cpu().numpy(), oc), "obs after masked reset"
+        for k, e in enumerate(walkers):
+            m, r, c = (7 * s + 31 * k) % 248, (37 * s + 5 * k) % 250, (11 * s + 3 * k) % 250
+            for h in (gpu, cpu) + (() if tiny_failed else (tiny,)):
+                h.write_mem(e, 0xD35E, [m])
+                h.write_mem(e, 0xD361, [r])
+                h.write_mem(e, 0xD362, [c])
         act = rng.integers(0, 8, n).astype(np.uint8)
         a = torch.from_numpy(act).cuda()
         gpu.step(a, og, rg, dg)
-        tiny.step(a, og, rg, dg)
         cpu.step(act, oc, rc, dc)
+        if not tiny_failed:
+            try:
+                tiny.step(a, ot, rg.clone(), dg.clone())
+            except _capi.GbEnvError as e:
+                assert "heat-map block pool" in str(e)
+                tiny_failed = True
+        assert np.array_equal(og.cpu().numpy(), oc), f"obs step {s}"
+        assert np.array_equal(rg.cpu().numpy(), rc), f"reward step {s}"
+    gpu.check()
     ig = torch.zeros((n, _capi.INFO_SCALARS), dtype=torch.float64, device="cuda")
     ic = np.zeros((n, _capi.INFO_SCALARS))
     gpu.get_info(ig)
     cpu.get_info(ic)
     assert np.array_equal(ig.cpu().numpy(), ic)
-    touched = 0
-    for e in (0, 7, n - 1):
-        m = cpu.counts_map(e)
-        touched = max(touched, int(np.count_nonzero(m)))
-        assert np.array_equal(gpu.counts_map(e), m), e
+    for e in (0, 1, 17, n - 1):
+        assert np.array_equal(gpu.counts_map(e), cpu.counts_map(e)), e
     assert gpu.counters().faults == 0
-    if touched > 14:  # 16 slots keep 2 free: envs that touched more cells report the overflow through `faults`
-        assert tiny.counters().faults > 0
+    if not tiny_failed:
+        with pytest.raises(_capi.GbEnvError, match="heat-map block pool"):
+            tiny.check()

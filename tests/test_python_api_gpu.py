@@ -62,11 +62,55 @@ def test_vec_environment_rollout_and_auto_reset(cuda_lib, roms):
     assert torch.equal(obs[..., 0], c[..., 0]) and torch.equal(obs[..., 1], c[..., 0]) and torch.equal(obs[..., 3], c[..., 1])
     full = vec.full_info(5)  # complete reference-shaped info dict for one env of the batch
     assert full["stats"]["step"] >= 1 and len(full["silph_co_events_aggregate"]) == 53
+    vec.close()
+
+
+def test_puffer_adaptor_contract(cuda_lib, oracle_lib, roms):
+    """PufferLib's vector contract (pufferlib.vector.Serial.send): an env that reported done is RESET on the next send -- its
+    action is ignored, it is not stepped, reward 0 / terminal False and the reset observation are delivered -- while the other
+    envs step.  Checked against the oracle driven the same way, env by env."""
+    import torch
+
+    from pokegym_b200 import VecEnvironment
+    from pokegym_b200.puffer import PufferVecAdaptor
+
+    n = 40
+    rom = roms("pokelike")
+    vec = VecEnvironment(n, rom, max_episode_steps=5)
     ad = PufferVecAdaptor(vec)
+    cpu = _capi.Handle(oracle_lib, n, rom)
+    cpu.tick(60, True)
+    oc, rc, dc = np.zeros((n, _capi.OBS_BYTES), np.uint8), np.zeros(n), np.zeros(n, np.uint8)
+    cpu.reset(oc, max_episode_steps=5)
     ad.async_reset()
-    ad.send(torch.zeros(n, dtype=torch.uint8, device="cuda"))
     flat, rew, term, trunc, infos, ids, mask = ad.recv()
-    assert flat.shape == (n, 23040) and len(ids) == n and mask.all()
+    assert flat.shape == (n, 23040) and len(ids) == n and mask.all() and np.array_equal(flat.cpu().numpy(), oc)
+    # stagger the episodes: envs 0..9 get a shorter first episode
+    short = np.zeros(n, np.uint8)
+    short[:10] = 1
+    vec.reset(mask=short, max_episode_steps=3)
+    vec.max_episode_steps = 5
+    cpu.reset(oc, mask=short, max_episode_steps=3)
+    pending = np.zeros(n, np.uint8)
+    rng = np.random.default_rng(9)
+    n_infos = 0
+    for t in range(14):
+        act = rng.integers(0, 8, n).astype(np.uint8)
+        ad.send(torch.from_numpy(act).cuda())
+        flat, rew, term, trunc, infos, ids, mask = ad.recv()
+        if pending.any():
+            cpu.reset(oc, mask=pending, max_episode_steps=5)
+        cpu.step_masked(act, pending, oc, rc, dc)
+        assert np.array_equal(rew.cpu().numpy(), rc), t
+        assert np.array_equal(term.cpu().numpy().astype(np.uint8), dc) and np.array_equal(trunc.cpu().numpy().astype(np.uint8), dc), t
+        assert np.array_equal(flat.cpu().numpy(), oc), t
+        assert (rc[pending.astype(bool)] == 0).all() and not dc[pending.astype(bool)].any()
+        assert len(infos) == int(dc.sum())
+        n_infos += len(infos)
+        pending = dc.copy()
+    assert n_infos >= n  # every env finished at least one episode
+    for e in (0, 9, 10, n - 1):
+        assert vec.save_state(e) == cpu.save_state(e)
     vec.close()
 
 
@@ -139,18 +183,25 @@ def test_error_paths_and_limits(cuda_lib, roms, monkeypatch):
             g.run_action(a)
         states.append([g.save_state(e) for e in (0, 13, 39)])
     assert states[0] == states[1] == states[2]
-    # visited-bitmap slots: an env that walks through more maps than it has slots raises the fault counter
-    monkeypatch.setenv("GBENV_VISITED_SLOTS", "2")
+    # exploration storage: a visited-bitmap pool that runs dry is an error, not a silent loss
+    monkeypatch.setenv("GBENV_VISITED_PAGES", "3")
     monkeypatch.setenv("GBENV_COUNTS_MAP", "0")
     s = _capi.Handle(cuda_lib, 2, rom)
     s.tick(30, True)
     rew = torch.zeros(2, dtype=torch.float64, device="cuda")
     done = torch.zeros(2, dtype=torch.uint8, device="cuda")
     obs2 = torch.zeros((2, _capi.OBS_BYTES), dtype=torch.uint8, device="cuda")
-    s.reset(obs2)
+    s.reset(obs2)  # one page per env
+    s.check()
     act = torch.zeros(2, dtype=torch.uint8, device="cuda")
-    for m in (1, 2, 3):
-        s.write_mem(1, 0xD35E, [m])  # teleport env 1 to another map
+    s.write_mem(1, 0xD35E, [1])  # teleport env 1 to another map: the third and last page
+    s.step(act, obs2, rew, done)
+    s.check()
+    s.write_mem(1, 0xD35E, [2])
+    s.step(act, obs2, rew, done)
+    with pytest.raises(_capi.GbEnvError, match="visited-bitmap page pool"):
+        s.check()
+    with pytest.raises(_capi.GbEnvError, match="exhausted"):
         s.step(act, obs2, rew, done)
     assert s.counters().faults == 1
     with pytest.raises(_capi.GbEnvError, match="exploration map"):
