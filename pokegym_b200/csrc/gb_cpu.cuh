@@ -21,20 +21,17 @@
 #include "gb_device.cuh"
 #include "gb_predecode.h"
 
-// tuning switches of the fast loop (tools/build_variants.sh builds A/B libraries; the defaults are the shipped choice)
-#ifndef GB_OPT_SYNCWARP
-#define GB_OPT_SYNCWARP 1       // explicit __syncwarp re-convergence in front of the write-back
-#endif
-#ifndef GB_OPT_DECLINE_FLAG
-#define GB_OPT_DECLINE_FLAG 1   // declines set a flag and leave at ONE exit (structured regions) instead of returning early
-#endif
-#ifndef GB_OPT_ONE_BODY
-#define GB_OPT_ONE_BODY 1       // one inlined instance of the instruction body for ROM and HRAM code
-#endif
-#ifndef GB_OPT_FLAG_DISPATCH
-#define GB_OPT_FLAG_DISPATCH 1  // INC/DEC and the arithmetic group are recognised by descriptor flag bits, not by handler id
-#endif
-
+// The fast loop exists in two builds, selected by the template parameter SIMT:
+//   SIMT = true  (k_run_frames, several envs per warp): whatever makes the instruction body decline only sets a flag and the
+//                one exit sits in front of the write-back.  Every divergent region is then single-entry / single-exit, nvcc
+//                gives each a re-convergence point, and the write-back, the stores and the loop tail run once per warp
+//                instead of once per handler group (measured before: 2.5 executions per iteration with 2.9 of 8 lanes).
+//   SIMT = false (k_run_frames_1, one env per single-thread block): declines return at once -- fewer instructions, and there
+//                is nothing to re-converge.
+// Measured on B200 (tools/gpu_variants.sh, env-steps/s): 4,096 envs, 1 lane: 127.0 k early-return / 120.8 k flag;
+// 32,768 envs, 16 lanes: 502 k early-return / 552 k flag; an explicit __syncwarp in front of the write-back added nothing
+// to the flag build (554 k) and cost 9 % at 1 lane.  One body for ROM + HRAM code and flag-bit dispatch of INC/DEC and the
+// arithmetic group help both (+4 % / +7 %).
 #if !defined(GB_TRACE_SLOT)
 #define GB_TRACE_SLOT(kind, phys, dx, dw)  // host-side convergence study only (tests/hostsim, -DGB_SLOT_TRACE)
 #endif
@@ -42,7 +39,7 @@
 __constant__ uint4 c_base_desc[512];  // per-opcode base descriptors (pd_build_base), uploaded once per process
 
 #define MODE_ATTN 0x8000u   // pending interrupt / HALT / PyBoy's interrupt_queued latch: the tick starts in cpu_attention
-#define MODE_POST 0x10000u  // HALT or a running TIMA: the tick ends in cpu_post_slow
+#define MODE_POST 0x10000u  // HALT: the tick ends in cpu_post_slow
 
 struct RunCtx {  // uniform per launch
     const uint4 *rom_dec;
@@ -50,16 +47,31 @@ struct RunCtx {  // uniform per launch
 };
 
 __device__ __forceinline__ uint32_t hot_mode(const Machine &m) {
-    const uint32_t attn = m.halted | m.iq | (m.iflag & m.ie & 0x1F), post = m.halted | (m.tmr & 0x04000000u);
+    const uint32_t attn = m.halted | m.iq | (m.iflag & m.ie & 0x1F), post = m.halted;
     return (attn ? MODE_ATTN : 0u) | (post ? MODE_POST : 0u);
 }
-// cycles until the interpreter has to stop for the LCD (the next hard event, see lcd_deadline)
-__device__ __forceinline__ int hot_rem(Machine &m) { return lcd_deadline(m); }
-// bring lcd.clock and the DIV counter up to the interpreter's countdown
+#define TIMA_ON 0x04000000u  // TAC bit 2 inside Machine.tmr
+// Cycles until the interpreter has to stop: for the LCD (the next hard event, see lcd_deadline) or, while TIMA runs, for the
+// tick in which Timer.tick's counter reaches the divider (PyBoy: one TIMA increment per CPU tick at most, so a counter that
+// is already past the divider fires again on the very next tick).
+// `fresh`: no executed tick is waiting for its share of the countdown: a counter already past the divider fires with the NEXT
+// tick (one instruction is let through).  After a slow tick (!fresh) the caller subtracts that tick's cycles, and a result <= 0
+// means that very tick fires -- also a 0-cycle interrupt dispatch on a counter that is past the divider.
+__device__ __forceinline__ int hot_rem(Machine &m, bool fresh) {
+    int rem = lcd_deadline(m);
+    if (m.tmr & TIMA_ON) {
+        int rt = (int)timer_divider(M_TAC(m)) - (int)m.timac;
+        if (fresh) rt = rt < 1 ? 1 : rt;
+        rem = rt < rem ? rt : rem;
+    }
+    return rem;
+}
+// bring lcd.clock, the DIV counter and (while TIMA runs) Timer.tick's TIMA counter up to the interpreter's countdown
 __device__ __forceinline__ void time_sync(Machine &m, int rem) {
     const uint32_t e = (uint32_t)(m.t_sync - rem);
     m.clock += e;
     m.divc += e;
+    if (m.tmr & TIMA_ON) m.timac += e;
     m.t_sync = rem;
 }
 
@@ -159,20 +171,17 @@ __device__ __forceinline__ bool fast_stack_push(uint32_t sp) { return sp - 0xC00
 // One instruction, given its control word.  FAST: returns false -- having changed nothing -- when the instruction needs
 // anything outside the fast set; `mode` is only read.  !FAST: always completes (full bus, every opcode).
 // Outputs: r (registers incl. pc), rom_off (bank switches), cyc, mode (HALT).
-// FAST: `grp` is the set of lanes that entered this loop iteration together (__activemask at its top) and `declined` may come in
-// already set (no descriptor could be fetched).  Every one of those lanes reaches the __syncwarp(grp) between the handler
-// and the write-back -- the body has no exit in front of it -- so the write-back, the stores and the loop tail are executed
-// once per warp again, however many handlers the lanes went through.  (nvcc gives the handler switch no reconvergence point of
-// its own: measured 2.5 executions of the write-back per iteration with 2.9 of 8 lanes each.)
-template <bool FAST>
+// FAST && SIMT: `declined` may come in already set (no descriptor could be fetched); the body has no exit in front of the
+// write-back.
+template <bool FAST, bool SIMT>
 __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &mode, uint32_t &cyc, uint8_t *memb,
-                                         const uint8_t *rom, uint32_t bank_mask, unsigned grp = 0, bool declined = false) {
+                                         const uint8_t *rom, uint32_t bank_mask, bool declined = false) {
     uint32_t bcde = r.bcde, hlaf = r.hlaf, sp = r.sp;
-#if GB_OPT_DECLINE_FLAG
-#define FAST_DECLINE() declined = true
-#else
-#define FAST_DECLINE() return false
-#endif
+#define FAST_DECLINE()         \
+    do {                       \
+        if (!SIMT) return false; \
+        declined = true;       \
+    } while (0)
     auto rd8 = [&](uint32_t a) -> uint32_t {  // Motherboard.getitem; FAST: WRAM (+ echo), ROM and HRAM, else decline
         if (FAST) {
             if (a - 0xC000u < 0x3E00u) return memb[mem_offset(MEM_WRAM + (a & 0x1FFF))];
@@ -201,7 +210,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         if (w & PDF_RD) {
             v = rd8(wa);
             if (w & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
-            if (FAST && !GB_OPT_DECLINE_FLAG && declined) return false;
+            if (FAST && !SIMT && declined) return false;
         }
     }
     // ---- handler
@@ -210,16 +219,16 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     cyc = d.x >> 24;
 #define PAIR_OPERAND() (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu)
     // The most frequent handlers are tested first, one compare each; the rest share a switch.
-    if ((w & PDF_MOV) || (FAST && GB_OPT_DECLINE_FLAG && declined)) {
+    if ((w & PDF_MOV) || (FAST && SIMT && declined)) {
         // plain moves (a third of all instructions) are done: rv = v
     } else if (w & PDF_JUMP) {
         if (((f ^ ex) & op) == 0) { next_pc = imm16; cyc += ex & 0xF; }
-    } else if (GB_OPT_FLAG_DISPATCH ? (w & PDF_INCDEC) != 0 : h == H_INCDEC) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
+    } else if (w & PDF_INCDEC) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
         const uint32_t b = v & 0xFF, sum = b + op, res = sum & 0xFF;
         const uint32_t nf = (f & FLAG_C) | ((((b ^ op ^ sum) & 0x10) << 1) ^ ex) | (res == 0 ? FLAG_Z : 0);
         rv = res | (nf << 8);
         wv = res;
-    } else if (GB_OPT_FLAG_DISPATCH ? (w & PDF_ARITH) != 0 : h == H_ARITH) {  // branch-free: a subtraction adds the complement and inverts the carries
+    } else if (w & PDF_ARITH) {  // branch-free: a subtraction adds the complement and inverts the carries
         const uint32_t a = (hlaf >> 16) & 0xFF, x = (v & 0xFF) ^ ex;
         const uint32_t sum = a + x + ((((f >> 4) & op) ^ ex) & 1);  // carry in for ADC / SBC only
         const uint32_t res = sum & 0xFF;
@@ -349,10 +358,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     }
     }
 #undef PAIR_OPERAND
-    if (FAST) {
-        if (GB_OPT_SYNCWARP) __syncwarp(grp);
-        if (declined) return false;  // nothing has been changed
-    }
+    if (FAST && declined) return false;  // nothing has been changed
 #undef FAST_DECLINE
     // ---- register write-back (uniform)
     r.bcde = gb_prmt(bcde, rv, d.z);
@@ -387,7 +393,9 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
 // One whole tick on the parked machine, for everything the fast loop declines: CPU.tick (interrupt check, HALT, one
 // instruction from anywhere, through the full bus) followed by Motherboard.tick's HALT fast-forward and Timer.tick's TIMA
 // half.  The caller has brought the clocks up to date; returns the T-cycles to advance them by.
-__device__ GB_NOINLINE uint32_t cpu_tick_slow(Machine &m, const uint4 *__restrict__ rom_dec, uint32_t bank_mask) {
+// While TIMA runs and the CPU is not halted the caller accounts the returned cycles to the TIMA counter lazily (time_sync);
+// a halted tick advances the timer here, by its fast-forwarded cycle count, and says so in `timer_ticked`.
+__device__ GB_NOINLINE uint32_t cpu_tick_slow(Machine &m, const uint4 *__restrict__ rom_dec, uint32_t bank_mask, uint32_t &timer_ticked) {
     uint32_t cyc = 0;
     bool execute = true;
     if (m.halted | m.iq | (m.iflag & m.ie & 0x1F)) {
@@ -402,11 +410,12 @@ __device__ GB_NOINLINE uint32_t cpu_tick_slow(Machine &m, const uint4 *__restric
         if ((d.x & 0xFF) == H_SLOW) d = cpu_decode_slow(m, pc);
         CpuRegs r = {m.bcde, m.hlaf, m.sp, pc};
         uint32_t rom_off = m.rom_off, mode = 0;
-        cpu_exec<false>(m, d, r, rom_off, mode, cyc, m.memb, m.rom, bank_mask);
+        cpu_exec<false, false>(m, d, r, rom_off, mode, cyc, m.memb, m.rom, bank_mask);
         m.bcde = r.bcde; m.hlaf = r.hlaf; m.sp = r.sp; m.pc = r.pc;
         m.n_instr++;
     }
-    if (m.halted | (m.tmr & 0x04000000u)) cyc = cpu_post_slow(m, cyc);
+    timer_ticked = m.halted;
+    if (m.halted) cyc = cpu_post_slow(m, cyc);
     return cyc;
 }
 
@@ -421,55 +430,42 @@ __device__ __forceinline__ uint4 cpu_decode_hram(const uint8_t *memb, uint32_t p
 
 // Interprets until this env's LCD clock reaches its next hard event (lcd_deadline).  `m` is the env's machine in shared
 // memory; the SM83 registers, the ROM bank offset, the cycle countdown and the mode word are cached in registers.
+template <bool SIMT>
 __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
     CpuRegs r = {m.bcde, m.hlaf, m.sp, m.pc};
     uint32_t rom_off = m.rom_off, n_instr = m.n_instr;
     uint8_t *memb = m.memb;
     const uint8_t *rom = m.rom;
-    int rem = hot_rem(m);
+    int rem = hot_rem(m, true);
     m.t_sync = rem;
-    uint32_t mode = hot_mode(m);
+    uint32_t mode = hot_mode(m), timer_pending = 0;
     do {
         // ---- fast loop: no call inside (a call in this loop makes the compiler save convergence-barrier state to the
         // stack on every iteration).  Left when the deadline is reached or an instruction needs the slow tick.
         for (;;) {
             uint32_t cyc;
-            const unsigned grp = GB_OPT_SYNCWARP ? __activemask() : 0u;
             // ONE instance of the instruction body: the descriptor comes from the pre-decoded ROM table or, for the HRAM stub,
-            // from an inline decode -- lanes running either kind of code meet again in front of cpu_exec.  A lane that has to
-            // leave the loop (interrupt pending, HALT, running TIMA, code in other RAM) goes through the body as `declined`.
+            // from an inline decode -- lanes running either kind of code meet again in front of cpu_exec.  SIMT: a lane that
+            // has to leave the loop (interrupt pending, HALT, running TIMA, code in other RAM) goes through the body as `declined`.
             uint4 d = make_uint4(H_SLOW, 0, 0x32103210u, 0);
             bool leave = false;
             const uint32_t pc = r.pc;
-#if GB_OPT_ONE_BODY
             if (!((pc | mode) & (0x8000u | MODE_POST))) {  // ROM code, nothing pending, not halted, TIMA stopped
                 d = __ldg(cx.rom_dec + (pc + (pc >> 14) * rom_off));
             } else if (!(mode & (MODE_ATTN | MODE_POST)) && pc - 0xFF80u < 0x7Du) {
                 d = cpu_decode_hram(memb, pc);
             } else {
-#if GB_OPT_DECLINE_FLAG
+                if (!SIMT) break;
                 leave = true;
-#else
-                break;
-#endif
             }
-            if (!cpu_exec<true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, grp, leave)) break;
-#else
-            (void)leave;
-            if (!((pc | mode) & (0x8000u | MODE_POST))) {
-                d = __ldg(cx.rom_dec + (pc + (pc >> 14) * rom_off));
-                if (!cpu_exec<true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, grp, false)) break;
-            } else if (!(mode & (MODE_ATTN | MODE_POST)) && pc - 0xFF80u < 0x7Du) {
-                d = cpu_decode_hram(memb, pc);
-                if (!cpu_exec<true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, grp, false)) break;
-            } else {
-                break;
-            }
-#endif
+            if (!cpu_exec<true, SIMT>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
             GB_TRACE_SLOT(0, pc < 0x8000u ? pc + (pc >> 14) * rom_off : (0xF00000u | pc), d.x, d.w);
             n_instr++;
             rem -= (int)cyc;
-            if (rem <= 0) goto deadline;
+            if (rem <= 0) {
+                timer_pending = 1;
+                goto deadline;
+            }
         }
         {
             // ---- slow tick.  Park the registers, bring the clocks up to date, apply the soft LCD events that have become due
@@ -479,10 +475,15 @@ __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
             time_sync(m, rem);
             if (m.lazy && (int)(m.clock - m.target) >= 0) lcd_catch_up(m);
             GB_TRACE_SLOT(1, m.pc < 0x8000u ? m.pc + (m.pc >> 14) * m.rom_off : (0xF00000u | m.pc), 0, 0);
-            const uint32_t cyc = cpu_tick_slow(m, cx.rom_dec, cx.bank_mask);
+            uint32_t timer_ticked;
+            const uint32_t cyc = cpu_tick_slow(m, cx.rom_dec, cx.bank_mask, timer_ticked);
             r.bcde = m.bcde; r.hlaf = m.hlaf; r.sp = m.sp; r.pc = m.pc; n_instr = m.n_instr; rom_off = m.rom_off;
             memb = m.memb; rom = m.rom;
-            rem = hot_rem(m);  // the tick may have changed what the countdown and the mode word derive from
+            // the tick's cycles reach clock / DIV / TIMA counter at the next time_sync; a halted tick has advanced the TIMA
+            // counter already: take them out again (modulo 2^32; the counter is only compared when it is in sync)
+            if (timer_ticked && (m.tmr & TIMA_ON)) m.timac -= cyc;
+            timer_pending = !timer_ticked;
+            rem = hot_rem(m, false);  // the tick may have changed what the countdown and the mode word derive from
             m.t_sync = rem;
             mode = hot_mode(m);
             rem -= (int)cyc;
@@ -491,4 +492,5 @@ __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
 deadline:
     m.bcde = r.bcde; m.hlaf = r.hlaf; m.sp = r.sp; m.pc = r.pc; m.n_instr = n_instr;
     time_sync(m, rem);
+    if (timer_pending) timer_tick_tima(m, 0);  // Timer.tick's TIMA half of the tick that ended here, unless a halted tick did it itself
 }

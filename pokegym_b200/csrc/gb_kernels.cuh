@@ -42,6 +42,7 @@ struct EnvSlot {
 // around LCD events: cpu_run_to_event interprets until this env's LCD clock reaches its next mode change, then the
 // mode change is performed (scanline parameters, rendering, LY/STAT/interrupt flags).  All envs see the same number
 // of LCD events per frame, so a warp re-converges 442 times a frame and the scanline renderer runs with every lane.
+template <bool SIMT>
 __device__ __forceinline__ void run_frames_env(Machine &m, const RunParams &p, int button) {
     RunCtx cx;
     cx.rom_dec = p.d.rom_dec;
@@ -65,7 +66,7 @@ __device__ __forceinline__ void run_frames_env(Machine &m, const RunParams &p, i
                 const int a = lcd_deadline(m);
                 if (a > 0) { m.divc += a; m.clock += a; }
             } else {
-                cpu_run_to_event(m, cx);
+                cpu_run_to_event<SIMT>(m, cx);
             }
             lcd_catch_up(m);
             done = m.frame_done;
@@ -92,7 +93,30 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
     machine_load(m, p.d, tile, lane);
     m.rline = line; m.rkeys = keys; m.rls = nslots;
     const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
-    run_frames_env(m, p, button);
+    run_frames_env<true>(m, p, button);
+    machine_store(m, p.d, tile, lane);
+    if (p.counters) {
+        atomicAdd(&p.counters[0], (unsigned long long)m.n_instr);
+        atomicAdd(&p.counters[1], (unsigned long long)m.n_cycles);
+        atomicAdd(&p.counters[2], (unsigned long long)p.n_frames);
+    }
+}
+
+// The same with ONE THREAD PER BLOCK, for batches small enough that every env gets a warp of its own anyway (lanes == 1:
+// up to 32 blocks x 148 SMs = 4,736 envs in one wave).  With __launch_bounds__(1) ptxas knows that no branch can diverge and
+// emits none of the convergence-barrier scaffolding (BSSY / BSYNC / BREAK / BMOV: about one instruction in nine of the
+// multi-lane build's hot loop), keeps loop-invariant addresses in uniform registers and needs no spills.
+__global__ void __launch_bounds__(1, 32) k_run_frames_1(RunParams p) {
+    const int env = blockIdx.x;
+    if (env >= p.d.n_envs || (p.skip && p.skip[env])) return;
+    const int tile = env >> 5, lane = env & 31;
+    EnvSlot &slot = *(EnvSlot *)((char *)s_env_slots);
+    uint32_t *const line = (uint32_t *)((char *)s_env_slots + ENV_SLOT_STRIDE), *const keys = line + FB_LINE_WORDS;
+    Machine &m = slot.m;
+    machine_load(m, p.d, tile, lane);
+    m.rline = line; m.rkeys = keys; m.rls = 1;
+    const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
+    run_frames_env<false>(m, p, button);
     machine_store(m, p.d, tile, lane);
     if (p.counters) {
         atomicAdd(&p.counters[0], (unsigned long long)m.n_instr);

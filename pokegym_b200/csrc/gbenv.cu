@@ -408,6 +408,12 @@ static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int re
     p.counters = h->d_counters;
     p.lanes = h->lanes;
     p.bank_mask = (h->d.rom_banks & (h->d.rom_banks - 1)) == 0 ? h->d.rom_banks - 1 : 0;
+    if (h->lanes == 1 && !getenv("GBENV_NO_SINGLE")) {  // one env per warp: the single-thread-block build of the same kernel
+        k_run_frames_1<<<h->n, 1, ENV_SMEM_BYTES(1), st>>>(p);
+        h->launches++;
+        CK(cudaGetLastError());
+        return GBENV_OK;
+    }
     int warps = (h->n + h->lanes - 1) / h->lanes;
     int blocks = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
     size_t smem = ENV_SMEM_BYTES((STEP_THREADS / 32) * h->lanes);

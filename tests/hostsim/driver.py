@@ -21,7 +21,7 @@ def build(force: bool = False) -> Path:
 
 
 class HostSim:
-    def __init__(self, n: int, rom: bytes):
+    def __init__(self, n: int, rom: bytes, simt: bool = True):
         self.dll = C.CDLL(str(build()))
         self.dll.hs_create.restype = C.c_void_p
         self.dll.hs_create.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
@@ -31,6 +31,8 @@ class HostSim:
             getattr(self.dll, name).argtypes = args
         self.n = n
         self.h = self.dll.hs_create(n, rom, len(rom))
+        self.dll.hs_set_simt.argtypes = [C.c_void_p, C.c_int]
+        self.dll.hs_set_simt(self.h, 1 if simt else 0)  # which build of the fast loop: k_run_frames (SIMT) or k_run_frames_1
 
     def close(self):
         if self.h:

@@ -35,6 +35,7 @@ struct HostSim {
     std::vector<uint8_t> rom;
     std::vector<uint4> rom_dec;
     unsigned long long counters[4] = {0, 0, 0, 0};
+    bool simt = true;  // which build of the fast loop hs_run steps (hs_set_simt)
 };
 
 static void scatter_image(HostSim *h, int env, const std::vector<uint32_t> &img, int version) {
@@ -74,6 +75,7 @@ void *hs_create(int n, const uint8_t *rom, size_t rom_len) {
 }
 
 void hs_destroy(void *p) { delete (HostSim *)p; }
+void hs_set_simt(void *p, int simt) { ((HostSim *)p)->simt = simt != 0; }
 
 int hs_load_blob(void *p, int env, const uint8_t *blob, size_t len) {
     HostSim *h = (HostSim *)p;
@@ -108,7 +110,8 @@ int hs_run(void *p, const uint8_t *actions, int n_frames, int render_mode) {
         machine_load(slot.m, rp.d, env >> 5, env & 31);
         const int button = actions ? c_action_button[actions[env] & 7] : -1;
         slot.m.rline = line; slot.m.rkeys = keys; slot.m.rls = 1;
-        run_frames_env(slot.m, rp, button);
+        if (h->simt) run_frames_env<true>(slot.m, rp, button);
+        else run_frames_env<false>(slot.m, rp, button);
         machine_store(slot.m, rp.d, env >> 5, env & 31);
         h->counters[0] += slot.m.n_instr; h->counters[1] += slot.m.n_cycles; h->counters[2] += n_frames;
     }

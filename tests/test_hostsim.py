@@ -34,13 +34,14 @@ def _compare(hs, cpu, n, where):
         assert hs.core_extra(e) == (x.stat_mode, x.ly_window, x.fault), where
 
 
+@pytest.mark.parametrize("simt", [True, False], ids=["simt", "single"])
 @pytest.mark.parametrize("rom_name,steps", [("pokelike", 10), ("conformance", 8), ("conformance_b", 6), ("pokelike_timer", 8), ("busy", 4),
                                             ("halt_edge", 30), ("lcd_probe", 10), ("lcd_probe_b", 10), ("divergent", 8)])
-def test_device_code_on_host_matches_oracle(hostsim, oracle_lib, roms, rom_name, steps):
+def test_device_code_on_host_matches_oracle(hostsim, oracle_lib, roms, rom_name, steps, simt):
     if rom_name not in synth_rom.rom_catalog():
         pytest.skip(f"{rom_name} ROM not in the catalog")
     rom, n = roms(rom_name), 5
-    hs, cpu = hostsim.HostSim(n, rom), _capi.Handle(oracle_lib, n, rom)
+    hs, cpu = hostsim.HostSim(n, rom, simt=simt), _capi.Handle(oracle_lib, n, rom)
     _compare(hs, cpu, n, "power-on")
     hs.tick(3, True)
     cpu.tick(3, True)

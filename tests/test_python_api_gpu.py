@@ -71,7 +71,7 @@ def test_puffer_adaptor_contract(cuda_lib, oracle_lib, roms):
     envs step.  Checked against the oracle driven the same way, env by env."""
     import torch
 
-    from pokegym_b200 import VecEnvironment
+    from pokegym_b200 import VecEnvironment, _capi
     from pokegym_b200.puffer import PufferVecAdaptor
 
     n = 40
