@@ -100,14 +100,37 @@ def kernel_source_hash() -> str:
     return h.hexdigest()[:16]
 
 
-def recorded_counters():
-    """ncu-derived per-launch counters of k_run_frames (tools/summarise_profile.py), or None when they are stale."""
-    p = ROOT / "profiles" / "kernel_counters.json"
+def recorded_counters(name="kernel_counters.json"):
+    """ncu-derived per-launch counters of the emulation kernel (tools/summarise_profile.py), or None when they are stale
+    (taken from another version of the CUDA sources)."""
+    p = ROOT / "profiles" / name
     try:
         d = json.load(open(p))
     except Exception:
         return None
     return d if d.get("kernel_source_hash") == kernel_source_hash() else None
+
+
+def issue_record(counters, kernel_ms, sm_mhz, n_sms):
+    """Instruction-issue view of a launch: SASS warp-instructions per emulated SM83 instruction and lanes active come from a
+    committed ncu capture of THIS kernel source (hash-stamped); the rates use this run's kernel time and clock."""
+    wi, emu = counters["warp_instructions_per_launch"], counters["emulated_instructions_per_launch"]
+    peak = n_sms * 4 * sm_mhz * 1e6
+    return {"kernel": counters.get("kernel"), "warp_instr_per_emulated_instr": wi / emu, "thread_instr_per_emulated_instr": wi * counters["lanes_active"] / emu,
+            "lanes_active_per_warp_instr": counters["lanes_active"], "warp_instr_per_s": wi / (kernel_ms / 1000.0), "peak_warp_instr_per_s": peak,
+            "frac": wi / (kernel_ms / 1000.0) / peak, "ncu_issue_active_pct": counters.get("issue_active_pct"), "ncu_alu_pipe_pct": counters.get("alu_pipe_pct"),
+            "ncu_sm_active_share_of_elapsed": counters.get("sm_active_share_of_elapsed"), "source": counters.get("source")}
+
+
+def tier_b_record():
+    """BASELINE.md tier B (the reference's unmodified wrapper over the oracle core, one process per core): measured where the
+    reference tree is mounted (tools/cpu_tier_b.py) and quoted from the committed file."""
+    for p in sorted((ROOT / "profiles").glob("*_cpu_tier_b.json"), reverse=True):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
 
 
 class ClockSampler:
@@ -284,7 +307,47 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU legs
 
-def run_leg(lib, rom, E, steps, warmup, preroll, dev, device_id, seed=7, state_path=None, mixed=False, lanes=None):
+def e2e_host_loop(h, E, n_e2e, world=1, dev=None):
+    """The same metric through gbenv_submit_host / gbenv_fetch_host with pinned host buffers: actions H2D and obs / reward / done
+    D2H inside the timed region, step t+1 submitted before the results of step t are fetched (two steps in flight), so the
+    observation copy overlaps the next emulation kernel -- what a vectoriser that keeps two rollout slots in flight does.
+    Returns env-steps/s of this rank's E envs (wall clock around the loop, max over ranks when world > 1)."""
+    import torch
+    import torch.distributed as dist
+
+    from pokegym_b200 import _capi
+
+    act_h = torch.randint(0, 8, (n_e2e + 4, E), dtype=torch.uint8).pin_memory()
+    obs_h = [torch.zeros((E, _capi.OBS_BYTES), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    rew_h = [torch.zeros(E, dtype=torch.float64).pin_memory() for _ in range(2)]
+    done_h = [torch.zeros(E, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def submit(i):
+        h.submit_host(act_h[i].numpy(), obs_h[i % 2].numpy(), rew_h[i % 2].numpy(), done_h[i % 2].numpy())
+
+    for i in range(3):
+        submit(i)
+        h.fetch_host()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    submit(3)
+    for i in range(4, 3 + n_e2e):
+        submit(i)        # step i queued behind step i-1 ...
+        h.fetch_host()   # ... while the results of step i-1 arrive (blocks until they are in the host buffers)
+        float(rew_h[(i - 1) % 2][0])  # the caller reads them
+    h.fetch_host()
+    float(rew_h[(2 + n_e2e) % 2][0])
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    return world * E * n_e2e / e2e_s
+
+
+def run_leg(lib, rom, E, steps, warmup, preroll, dev, device_id, seed=7, state_path=None, mixed=False, lanes=None, e2e_steps=0):
     """One single-GPU workload: E envs, device-resident actions, obs into a 4-deep device ring.  CUDA-event timed."""
     import torch
 
@@ -317,7 +380,14 @@ def run_leg(lib, rom, E, steps, warmup, preroll, dev, device_id, seed=7, state_p
     rec = {"envs_per_gpu": E, "value": E * steps / (ms / 1000.0), "unit": "env-steps/s", "steps": steps, "warmup": warmup, "preroll": preroll,
            "ms_per_step": ms / steps, "kernel_ms": (k1[0] - k0[0]) / max(1, k1[1] - k0[1]),
            "emulated_instr_per_s": (c1.instructions - c0.instructions) / (ms / 1000.0),
-           "emulated_instr_per_env_step": (c1.instructions - c0.instructions) / (E * steps), "faults": int(c1.faults)}
+           "emulated_instr_per_env_step": (c1.instructions - c0.instructions) / (E * steps), "faults": int(c1.faults), "lanes_per_warp": h.lanes_per_warp()}
+    if e2e_steps:
+        del ring
+        torch.cuda.empty_cache()
+        v = e2e_host_loop(h, E, e2e_steps)
+        rec["e2e"] = {"value": v, "unit": "env-steps/s", "steps": e2e_steps, "h2d_bytes_per_step": E, "d2h_bytes_per_step": E * (_capi.OBS_BYTES + 8 + 1),
+                      "share_of_value": v / rec["value"], "api": "gbenv_submit_host / gbenv_fetch_host (pinned host buffers, two steps in flight)"}
+        ring = None
     h.close()
     del ring
     torch.cuda.empty_cache()
@@ -397,8 +467,11 @@ def main():
     # GBENV_LIB: A/B builds of the kernel while tuning (tools/quick_bench.sh); the judged runs use the in-tree library
     lib = _capi.GbEnvLib(os.environ.get("GBENV_LIB") or (g.build_cuda() if rank == 0 or not _capi.DEFAULT_LIB.exists() else _capi.DEFAULT_LIB))
     if args.only_leg:
+        if args.only_leg.startswith("custom:"):  # custom:rom,envs,steps,warmup,preroll,mixed  (tuning sweeps)
+            f = args.only_leg[7:].split(",")
+            LEGS[args.only_leg] = (f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), bool(int(f[5])))
         rom_name, E, steps, warmup, preroll, mixed = LEGS[args.only_leg]
-        rec = run_leg(lib, build_rom(rom_name), E, steps, warmup, preroll, dev, local_rank, mixed=mixed)
+        rec = run_leg(lib, build_rom(rom_name), E, steps, warmup, preroll, dev, local_rank, mixed=mixed, e2e_steps=8 if args.only_leg == "envs_32768" else 0)
         rec["leg"] = args.only_leg
         print(json.dumps(rec))
         return
@@ -467,34 +540,7 @@ def main():
     # buffered: step t+1 is submitted before the results of step t are fetched, so the 94 MB D2H of the observations
     # overlaps the next emulation kernel -- what a vectoriser that keeps two rollout slots in flight does.
     n_e2e = max(3, min(args.e2e_steps, K))
-    act_h = torch.randint(0, 8, (n_e2e + 4, E), dtype=torch.uint8).pin_memory()
-    obs_h = [torch.zeros((E, _capi.OBS_BYTES), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    rew_h = [torch.zeros(E, dtype=torch.float64).pin_memory() for _ in range(2)]
-    done_h = [torch.zeros(E, dtype=torch.uint8).pin_memory() for _ in range(2)]
-
-    def submit(i):
-        h.submit_host(act_h[i].numpy(), obs_h[i % 2].numpy(), rew_h[i % 2].numpy(), done_h[i % 2].numpy())
-
-    for i in range(3):
-        submit(i)
-        h.fetch_host()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    submit(3)
-    for i in range(4, 3 + n_e2e):
-        submit(i)        # step i queued behind step i-1 ...
-        h.fetch_host()   # ... while the results of step i-1 arrive (blocks until they are in the host buffers)
-        float(rew_h[(i - 1) % 2][0])  # the caller reads them
-    h.fetch_host()
-    float(rew_h[(2 + n_e2e) % 2][0])
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * E * n_e2e / e2e_s
+    e2e_value = e2e_host_loop(h, E, n_e2e, world, dev)
 
     if rank != 0:
         if world > 1:
@@ -529,15 +575,7 @@ def main():
         "faults": int(c1.faults),
     }
     if counters and counters.get("envs_per_launch") == E:
-        # instruction-issue view of the same kernel: SASS warp-instructions per emulated SM83 instruction and lanes active
-        # come from the committed ncu capture of THIS kernel source (hash-stamped); rates from this run's clock
-        wi = counters["warp_instructions_per_launch"]
-        emu = counters["emulated_instructions_per_launch"]
-        issue_peak = props.multi_processor_count * 4 * sm_mhz * 1e6
-        line["issue"] = {"warp_instr_per_emulated_instr": wi / emu, "thread_instr_per_emulated_instr": wi * counters["lanes_active"] / emu,
-                         "lanes_active_per_warp_instr": counters["lanes_active"], "warp_instr_per_s": wi / (run_ms / 1000.0),
-                         "peak_warp_instr_per_s": issue_peak, "frac": wi / (run_ms / 1000.0) / issue_peak,
-                         "ncu_issue_active_pct": counters.get("issue_active_pct"), "source": counters.get("source")}
+        line["issue"] = issue_record(counters, run_ms, sm_mhz, props.multi_processor_count)
     want = [] if args.legs == "none" else ([x for x in LEGS if x != "main_4096"] if args.legs == "all" else [x for x in args.legs.split(",") if x in LEGS])
     if world == 1 and want:
         h.close()
@@ -547,8 +585,12 @@ def main():
         for name in want:
             rom_name, E2, steps, warmup, preroll, mixed = LEGS[name]
             try:
-                rec = run_leg(lib, rom if rom_name == args.rom else build_rom(rom_name), E2, steps, warmup, preroll, dev, local_rank, mixed=mixed)
+                rec = run_leg(lib, rom if rom_name == args.rom else build_rom(rom_name), E2, steps, warmup, preroll, dev, local_rank, mixed=mixed,
+                              e2e_steps=8 if name == "envs_32768" else 0)
                 rec["workload"] = f"{rom_name} ROM" + (", env i reset from reference save-state i mod 40 (BASELINE.json config 5)" if mixed else "")
+                lc = recorded_counters(f"r2_{name}_counters.json")
+                if lc and lc.get("envs_per_launch") == E2:
+                    rec["issue"] = issue_record(lc, rec["kernel_ms"], sm_mhz, props.multi_processor_count)
                 line["legs"][name] = rec
             except Exception as e:
                 line["legs"][name] = {"error": str(e)}
@@ -568,6 +610,10 @@ def main():
             line["legs"]["divergent_4096"]["cpu_baseline"] = {"value": v2, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": s2}
     except Exception as e:  # the baseline is reported, never required for the GPU number
         line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    tb = tier_b_record()
+    if tb:
+        line["cpu_baseline_tier_b"] = tb
+    line["pyboy_baseline"] = "not run (PyBoy / Pokemon Red ROM missing): cpu_baseline is the oracle port, tier B the reference wrapper over it"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

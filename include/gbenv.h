@@ -74,6 +74,7 @@ int gbenv_check(gbenv_t *h);
 /* Tuning knob: envs carried by each warp of the emulation kernel (1..32).  The default is
  * chosen from n_envs and the SM count so that a small batch still fills the GPU with warps.        */
 int gbenv_set_lanes_per_warp(gbenv_t *h, int lanes);
+int gbenv_get_lanes_per_warp(const gbenv_t *h); /* the value in use (>= 1), or a negative error code */
 
 /* ---- (4) reset from PyBoy .state files ------------------------------------------------------
  * replaces pyboy_binding.open_state_file / load_pyboy_state (:59-69).  A blob is parsed ONCE on

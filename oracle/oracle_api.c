@@ -23,6 +23,7 @@ typedef struct oracle_env {
     int initial_template;
 } oracle_env;
 
+typedef struct par_pool par_pool;
 typedef struct oracle {
     int n;
     uint8_t *rom;
@@ -32,10 +33,12 @@ typedef struct oracle {
     size_t *template_len;
     int n_templates;
     int threads;
+    struct par_pool *pool; /* persistent worker threads (par_for) */
     char err[256];
 } oracle;
 
 static char g_err[256] = "";
+static void par_pool_stop(oracle *h);
 
 static int fail(oracle *h, int code, const char *msg) {
     snprintf(h ? h->err : g_err, 256, "%s", msg);
@@ -61,6 +64,7 @@ int oracle_create(int n_envs, const uint8_t *rom, size_t rom_len, int device_id,
         h->envs[e].initial_template = -1;
     }
     h->threads = 0;
+    h->pool = NULL;
     *out = h;
     return GBENV_OK;
 }
@@ -73,6 +77,7 @@ int oracle_set_threads(oracle *h, int threads) {
 
 int oracle_destroy(oracle *h) {
     if (!h) return GBENV_E_ARG;
+    par_pool_stop(h);
     for (int e = 0; e < h->n; e++) pg_wrapper_free(&h->envs[e].wrap);
     for (int t = 0; t < h->n_templates; t++) free(h->templates[t]);
     free(h->templates);
@@ -146,40 +151,96 @@ static int nthreads(const oracle *h) {
     return n > 0 ? (int)n : 1;
 }
 
-/* tiny pthread parallel-for over envs (OpenMP is not usable with every gcc in this image) */
+/* Persistent worker pool: a parallel-for over envs (OpenMP is not usable with every gcc in this image).  The workers are
+ * created on first use and sleep on a condition variable between jobs, so a step costs no thread start-up; envs are handed
+ * out dynamically through an atomic counter. */
 typedef void (*env_fn)(oracle *h, int e, void *ctx);
-typedef struct par_job {
+struct par_pool {
+    pthread_t th[256];
+    int n_threads;
+    pthread_mutex_t mu;
+    pthread_cond_t go, done;
+    unsigned long generation; /* bumped per job */
+    int running;              /* workers still inside the current job */
+    int quit;
     oracle *h;
     env_fn fn;
     void *ctx;
-    int next;
-    pthread_mutex_t mu;
-} par_job;
+    int next; /* next env to hand out (atomic) */
+};
+
+static void par_drain(par_pool *p) {
+    for (;;) {
+        int e = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
+        if (e >= p->h->n) break;
+        p->fn(p->h, e, p->ctx);
+    }
+}
 
 static void *par_worker(void *arg) {
-    par_job *j = (par_job *)arg;
+    par_pool *p = (par_pool *)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&p->mu);
     for (;;) {
-        pthread_mutex_lock(&j->mu);
-        int e = j->next++;
-        pthread_mutex_unlock(&j->mu);
-        if (e >= j->h->n) break;
-        j->fn(j->h, e, j->ctx);
+        while (!p->quit && p->generation == seen) pthread_cond_wait(&p->go, &p->mu);
+        if (p->quit) break;
+        seen = p->generation;
+        pthread_mutex_unlock(&p->mu);
+        par_drain(p);
+        pthread_mutex_lock(&p->mu);
+        if (--p->running == 0) pthread_cond_signal(&p->done);
     }
+    pthread_mutex_unlock(&p->mu);
     return NULL;
+}
+
+static void par_pool_stop(oracle *h) {
+    par_pool *p = h->pool;
+    if (!p) return;
+    pthread_mutex_lock(&p->mu);
+    p->quit = 1;
+    pthread_cond_broadcast(&p->go);
+    pthread_mutex_unlock(&p->mu);
+    for (int i = 0; i < p->n_threads; i++) pthread_join(p->th[i], NULL);
+    pthread_mutex_destroy(&p->mu);
+    pthread_cond_destroy(&p->go);
+    pthread_cond_destroy(&p->done);
+    free(p);
+    h->pool = NULL;
 }
 
 static void par_for(oracle *h, env_fn fn, void *ctx) {
     int t = nthreads(h);
     if (t > h->n) t = h->n;
+    if (t > 256) t = 256;
     if (t <= 1) {
         for (int e = 0; e < h->n; e++) fn(h, e, ctx);
         return;
     }
-    par_job j = {h, fn, ctx, 0, PTHREAD_MUTEX_INITIALIZER};
-    pthread_t th[256];
-    if (t > 256) t = 256;
-    for (int i = 0; i < t; i++) pthread_create(&th[i], NULL, par_worker, &j);
-    for (int i = 0; i < t; i++) pthread_join(th[i], NULL);
+    if (h->pool && h->pool->n_threads != t - 1) par_pool_stop(h); /* oracle_set_threads changed the width */
+    if (!h->pool) {
+        par_pool *p = (par_pool *)calloc(1, sizeof(par_pool));
+        pthread_mutex_init(&p->mu, NULL);
+        pthread_cond_init(&p->go, NULL);
+        pthread_cond_init(&p->done, NULL);
+        p->h = h;
+        p->n_threads = t - 1; /* the calling thread works too */
+        for (int i = 0; i < p->n_threads; i++) pthread_create(&p->th[i], NULL, par_worker, p);
+        h->pool = p;
+    }
+    par_pool *p = h->pool;
+    pthread_mutex_lock(&p->mu);
+    p->fn = fn;
+    p->ctx = ctx;
+    __atomic_store_n(&p->next, 0, __ATOMIC_RELAXED);
+    p->running = p->n_threads;
+    p->generation++;
+    pthread_cond_broadcast(&p->go);
+    pthread_mutex_unlock(&p->mu);
+    par_drain(p);
+    pthread_mutex_lock(&p->mu);
+    while (p->running) pthread_cond_wait(&p->done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
 }
 
 typedef struct run_ctx {
@@ -351,6 +412,7 @@ int oracle_last_kernel_ms(oracle *h, int which, float *ms) {
     return GBENV_OK;
 }
 
+int oracle_get_lanes_per_warp(const oracle *h) { return h ? 1 : GBENV_E_ARG; }
 int oracle_set_lanes_per_warp(oracle *h, int lanes) {
     (void)lanes;
     return h ? GBENV_OK : GBENV_E_ARG;

@@ -64,6 +64,7 @@ _SIGS = {
     "sync": ([C.c_void_p], C.c_int),
     "check": ([C.c_void_p], C.c_int),
     "set_lanes_per_warp": ([C.c_void_p, C.c_int], C.c_int),
+    "get_lanes_per_warp": ([C.c_void_p], C.c_int),
     "add_state_template": ([C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)], C.c_int),
     "load_template": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int], C.c_int),
     "set_initial_template": ([C.c_void_p, C.c_void_p, C.c_int, C.c_int], C.c_int),
@@ -255,6 +256,9 @@ class Handle:
     def check(self):
         """sync + raise if a pool of the exploration storage (visited bitmaps / heat maps) ran dry"""
         self._check(self.lib.check(self._h), "check")
+
+    def lanes_per_warp(self) -> int:
+        return int(self.lib.get_lanes_per_warp(self._h))
 
     def set_lanes_per_warp(self, lanes: int):
         self._check(self.lib.set_lanes_per_warp(self._h, int(lanes)), "set_lanes_per_warp")

@@ -139,6 +139,15 @@ __device__ GB_NOINLINE uint32_t cpu_post_slow(Machine &m, uint32_t cycles) {
         const bool sleeps_on = (m.lcdc & 0x80) && !(m.iflag & m.ie & 0x1F);
         const int a = sleeps_on ? lcd_deadline(m) : (int)(m.target - m.clock), b = timer_cycles_to_interrupt(m), c = a < b ? a : b;
         cycles = c < 0 ? 0u : (uint32_t)c;
+        if ((m.tmr & 0x04000000u) && b <= 0 && !(m.iflag & m.ie & 0x1F)) {
+            // The TIMA counter is so far past the divider that the timer interrupt is "due" (PyBoy: cycles_to_interrupt <= 0):
+            // the halted CPU now spins through 0-cycle ticks, each incrementing TIMA once, until TIMA overflows -- nothing else
+            // changes meanwhile (no cycles pass, nothing is pending).  All but the last of those 0x100 - TIMA ticks are applied
+            // here in closed form; the last one, the overflow, is the timer_tick_tima below.
+            const uint32_t n = 0xFFu - M_TIMA(m);
+            m.timac -= n * timer_divider(M_TAC(m));
+            m.tmr |= 0xFF00u;
+        }
     }
     timer_tick_tima(m, cycles);
     return cycles;
@@ -358,6 +367,16 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     }
     }
 #undef PAIR_OPERAND
+#if !defined(GB_HOSTSIM) && !defined(GB_OPT_NO_JOIN)
+    if (FAST && SIMT) {
+        // Opaque join: the empty asm keeps nvcc from threading the handlers that cannot decline straight to the write-back,
+        // past this test.  With every path through here, this point post-dominates the handler dispatch and gets a
+        // re-convergence barrier (BSYNC): the write-back, the stores and the loop tail run once per warp.
+        uint32_t dj = declined;
+        asm volatile("" : "+r"(dj));
+        declined = dj != 0;
+    }
+#endif
     if (FAST && declined) return false;  // nothing has been changed
 #undef FAST_DECLINE
     // ---- register write-back (uniform)
@@ -439,6 +458,7 @@ __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
     int rem = hot_rem(m, true);
     m.t_sync = rem;
     uint32_t mode = hot_mode(m), timer_pending = 0;
+again:
     do {
         // ---- fast loop: no call inside (a call in this loop makes the compiler save convergence-barrier state to the
         // stack on every iteration).  Left when the deadline is reached or an instruction needs the slow tick.
@@ -493,4 +513,16 @@ deadline:
     m.bcde = r.bcde; m.hlaf = r.hlaf; m.sp = r.sp; m.pc = r.pc; m.n_instr = n_instr;
     time_sync(m, rem);
     if (timer_pending) timer_tick_tima(m, 0);  // Timer.tick's TIMA half of the tick that ended here, unless a halted tick did it itself
+    if ((m.tmr & TIMA_ON) && !m.halted) {
+        // a running TIMA ends the countdown at every increment (every 16 cycles at the fastest rate): unless the LCD is due as
+        // well, re-arm the countdown and carry on instead of going back through the frame loop
+        const bool lcd_due = (m.lcdc & 0x80) ? (int)(m.clock - m.target) >= 0 : m.clock >= FRAME_CYCLES;
+        if (!lcd_due) {
+            rem = hot_rem(m, true);
+            m.t_sync = rem;
+            mode = hot_mode(m);
+            timer_pending = 0;
+            if (rem > 0) goto again;
+        }
+    }
 }

@@ -232,8 +232,11 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
         const int resident_warps = sms * STEP_MIN_BLOCKS * (STEP_THREADS / 32);
         // measured on B200 (tools/quick_bench.sh): the smallest power of two that keeps every warp resident wins; counts
         // that are not powers of two make warps straddle 32-env tiles (partial 128-byte lines) and lose 3-5 %
+        // and past one env per warp, the next power of two (half a wave of warps) wins: 8,192 envs 198 k env-steps/s at 4
+        // lanes vs 181 k at 2; 16,384: 339 k at 8 vs 304 k at 4; 32,768: 578 k at 16 vs 522 k at 8; 65,536: 957 k at 32 vs 924 k at 16
         int lanes = 1;
-        while (lanes < 32 && (n_envs + lanes - 1) / lanes > resident_warps) lanes <<= 1;
+        if (n_envs > resident_warps)
+            while (lanes < 32 && (n_envs + lanes - 1) / lanes > resident_warps / 2) lanes <<= 1;
         if (const char *ev = getenv("GBENV_LANES")) {
             int v = atoi(ev);
             if (v >= 1 && v <= 32) lanes = v;
@@ -318,6 +321,8 @@ extern "C" int gbenv_set_lanes_per_warp(gbenv *h, int lanes) {
     h->lanes = lanes;
     return GBENV_OK;
 }
+
+extern "C" int gbenv_get_lanes_per_warp(const gbenv *h) { return h ? h->lanes : GBENV_E_ARG; }
 
 extern "C" int gbenv_sync(gbenv *h) {
     if (!h) return GBENV_E_ARG;
