@@ -165,14 +165,36 @@ struct CpuRegs {
 #define FAST_WR_NONE 0xFFFFFFFFu
 #define FAST_WR_DROP 0xFFFFFFFEu
 #define FAST_WR_BANK 0xFFFFFFFDu
+#define FAST_WR_P1 0xFFFFFFFCu  // the joypad select register: the stored byte is Interaction.pull of the written one
 __device__ __forceinline__ uint32_t mem_offset(uint32_t i) { return ((i >> 2) << 7) | (i & 3); }
-__device__ __forceinline__ uint32_t fast_store_target(uint32_t a) {
+__device__ __forceinline__ uint32_t fast_store_target(uint32_t a) {  // single-lane build: first match wins
     if (a - 0xC000u < 0x3E00u) return mem_offset(MEM_WRAM + (a & 0x1FFF));                               // WRAM and its echo
     if (a - 0xFF80u < 0x7Fu || a - 0xFE00u < 0x100u) return mem_offset(MEM_HI + (a - 0xFE00));             // HRAM, OAM
     if (a - 0x8000u < 0x2000u) return mem_offset(MEM_VRAM + (a - 0x8000));                                // VRAM
     if (a - 0x2000u < 0x2000u) return FAST_WR_BANK;
     if (a - 0xFF10u < 0x30u) return FAST_WR_DROP;
+    if (a == 0xFF00u) return FAST_WR_P1;
     return FAST_WR_NONE;
+}
+// Plain RAM behind address `a`: work RAM and its echo, VRAM, OAM / 0xFEA0-0xFEFF, HRAM (0xFF80-0xFFFE).  Returns whether it
+// is, and the byte offset inside the env's interleaved array (meaningless otherwise).  Selects only.
+__device__ __forceinline__ bool fast_plain_offset(uint32_t a, uint32_t &off) {
+    const bool wram = a - 0xC000u < 0x3E00u, vram = a - 0x8000u < 0x2000u;
+    const bool hi = (a - 0xFE00u < 0x100u) | (a - 0xFF80u < 0x7Fu);
+    const uint32_t i = wram ? MEM_WRAM + (a & 0x1FFF) : a + (vram ? MEM_VRAM - 0x8000u : MEM_HI - 0xFE00u);
+    off = mem_offset(i);
+    return wram | vram | hi;
+}
+// byte at base + off when `ok`, else `otherwise`: a predicated load (no branch: the lanes of a warp stay together whatever
+// kind of memory each of them reads)
+__device__ __forceinline__ uint32_t fast_load_u8(const uint8_t *base, uint32_t off, bool ok, uint32_t otherwise) {
+#if defined(GB_HOSTSIM)
+    return ok ? base[off] : otherwise;
+#else
+    uint32_t r = otherwise;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.u8 %0, [%1];\n\t}" : "+r"(r) : "l"(base + off), "r"((uint32_t)ok) : "memory");
+    return r;
+#endif
 }
 // both bytes of a push below `sp` inside work RAM (or its echo)
 __device__ __forceinline__ bool fast_stack_push(uint32_t sp) { return sp - 0xC002u < 0x3DFFu; }
@@ -195,7 +217,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         if (FAST) {
             if (a - 0xC000u < 0x3E00u) return memb[mem_offset(MEM_WRAM + (a & 0x1FFF))];
             if (a < 0x8000u) return __ldg(rom + (a + (a >> 14) * rom_off));
-            if (a - 0xFF80u < 0x7Fu) return memb[mem_offset(MEM_HI + (a - 0xFE00))];
+            if (a - 0xFF80u < 0x7Fu || a - 0xFF00u < 4u) return memb[mem_offset(MEM_HI + (a - 0xFE00))];  // HRAM; P1, SB, SC
             declined = true;
             return 0;
         }
@@ -212,14 +234,39 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     if (w & (PDF_RD | PDF_WR)) {
         wa = (w & PDF_AIMM) ? (d.y & 0xFFFFu) : (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu);
         if (w & PDF_ASP) wa = sp;
-        if (FAST && (w & PDF_WR)) {
-            wt = fast_store_target(wa);
-            if (wt == FAST_WR_NONE) FAST_DECLINE();
-        }
-        if (w & PDF_RD) {
-            v = rd8(wa);
-            if (w & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
-            if (FAST && !SIMT && declined) return false;
+        if (FAST && SIMT) {
+            // ONE straight-line classification of the address serves the read and the deferred store: plain RAM (work RAM
+            // and its echo, VRAM, OAM / 0xFEA0-0xFEFF, HRAM -- Motherboard.getitem / setitem touch nothing else for these)
+            // is an offset into this env's interleaved array, ROM a pointer into the shared image; selects, no branches
+            uint32_t off;
+            const bool plain = fast_plain_offset(wa, off);
+            if (w & PDF_WR) {
+                wt = plain ? off : (wa - 0x2000u < 0x2000u) ? FAST_WR_BANK : (wa - 0xFF10u < 0x30u) ? FAST_WR_DROP : wa == 0xFF00u ? FAST_WR_P1 : FAST_WR_NONE;
+                if (wt == FAST_WR_NONE) FAST_DECLINE();
+            }
+            if (w & PDF_RD) {
+                // P1 (the byte Interaction.pull left there), SB, SC and 0xFF03 read back from the IO array like plain RAM
+                const bool in_rom = wa < 0x8000u, ok = plain | in_rom | (wa - 0xFF00u < 4u);
+                v = fast_load_u8(in_rom ? rom : memb, in_rom ? wa + (wa >> 14) * rom_off : off, ok, v);
+                if (!ok) declined = true;
+                if (w & PDF_RD16) {  // POP / RET: the second byte, classified the same way
+                    const uint32_t wb = (wa + 1) & 0xFFFF;
+                    uint32_t off2;
+                    const bool plain2 = fast_plain_offset(wb, off2), in_rom2 = wb < 0x8000u, ok2 = plain2 | in_rom2 | (wb - 0xFF00u < 4u);
+                    v |= fast_load_u8(in_rom2 ? rom : memb, in_rom2 ? wb + (wb >> 14) * rom_off : off2, ok2, 0) << 8;
+                    if (!ok2) declined = true;
+                }
+            }
+        } else {  // single-lane build: branches are free (nothing diverges), the first matching region wins
+            if (FAST && (w & PDF_WR)) {
+                wt = fast_store_target(wa);
+                if (wt == FAST_WR_NONE) FAST_DECLINE();
+            }
+            if (w & PDF_RD) {
+                v = rd8(wa);
+                if (w & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
+                if (FAST && declined) return false;
+            }
         }
     }
     // ---- handler
@@ -227,22 +274,37 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     uint32_t rv = v, next_pc = d.y >> 16, wv = v, wn = w & PDF_WR;
     cyc = d.x >> 24;
 #define PAIR_OPERAND() (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu)
-    // The most frequent handlers are tested first, one compare each; the rest share a switch.
-    if ((w & PDF_MOV) || (FAST && SIMT && declined)) {
-        // plain moves (a third of all instructions) are done: rv = v
-    } else if (w & PDF_JUMP) {
+    // SIMT: conditional / unconditional jumps are predicated, not dispatched (two selects on every lane), plain moves need no
+    // handler at all, and INC / DEC and the ADD ADC SUB SBC CP group share ONE adder body (selects pick the operands): a warp
+    // whose lanes run a mix of the four most frequent kinds of instruction takes a single path through here.
+    // Single lane: one compare per kind, most frequent first, each with its own minimal body.
+    const bool jump_taken = SIMT && (w & PDF_JUMP) && ((f ^ ex) & op) == 0;
+    if (SIMT) {
+        next_pc = jump_taken ? imm16 : next_pc;
+        cyc += jump_taken ? (ex & 0xF) : 0u;
+    }
+    if ((w & PDF_MOV) || (SIMT && (w & PDF_JUMP)) || (FAST && SIMT && declined)) {
+        // rv = v
+    } else if (!SIMT && (w & PDF_JUMP)) {
         if (((f ^ ex) & op) == 0) { next_pc = imm16; cyc += ex & 0xF; }
-    } else if (w & PDF_INCDEC) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
+    } else if (!SIMT && (w & PDF_INCDEC)) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
         const uint32_t b = v & 0xFF, sum = b + op, res = sum & 0xFF;
         const uint32_t nf = (f & FLAG_C) | ((((b ^ op ^ sum) & 0x10) << 1) ^ ex) | (res == 0 ? FLAG_Z : 0);
         rv = res | (nf << 8);
         wv = res;
-    } else if (w & PDF_ARITH) {  // branch-free: a subtraction adds the complement and inverts the carries
-        const uint32_t a = (hlaf >> 16) & 0xFF, x = (v & 0xFF) ^ ex;
-        const uint32_t sum = a + x + ((((f >> 4) & op) ^ ex) & 1);  // carry in for ADC / SBC only
-        const uint32_t res = sum & 0xFF;
-        const uint32_t nf = (((((a ^ x ^ sum) & 0x10) << 1) | ((sum >> 4) & 0x10)) ^ (ex & 0x30)) | (ex & FLAG_N) | (res == 0 ? FLAG_Z : 0);
-        rv = res | (nf << 8);
+    } else if (w & (PDF_INCDEC | PDF_ARITH)) {
+        // a + x + cin with  INC / DEC: a = v, x = +1 / -1 (mod 256), no carry in, C kept, ex = 0 / N|H (DEC inverts the half carry
+        // like a subtraction);  ADD..CP: a = A, x = v or its complement (ex = 0 / 0xFF), carry in for ADC / SBC (inverted for
+        // the subtractions, whose H and C are the inverted carries)
+        const bool inc = SIMT && (w & PDF_INCDEC) != 0;
+        const uint32_t b = v & 0xFF;
+        const uint32_t a = inc ? b : ((hlaf >> 16) & 0xFF), x = inc ? op : (b ^ ex);
+        const uint32_t cin = inc ? 0u : ((((f >> 4) & op) ^ ex) & 1);
+        const uint32_t sum = a + x + cin, res = sum & 0xFF;
+        const uint32_t hn = (((a ^ x ^ sum) & 0x10) << 1) ^ (ex & 0x60);
+        const uint32_t cb = inc ? (f & FLAG_C) : (((sum >> 4) ^ ex) & 0x10);
+        rv = res | ((hn | cb | (res == 0 ? FLAG_Z : 0)) << 8);
+        wv = res;
     } else if (h == H_HLI) {
         rv = ((PAIR_OPERAND() + gb_prmt(d.x, 0, 0x9991)) & 0xFFFFu) | (v << 16);  // + sign-extended op
     } else switch (h) {
@@ -262,6 +324,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         if (((f ^ ex) & op) == 0) {  // high byte at SP-1 first, then low byte at SP-2
             if (FAST && !fast_stack_push(sp)) FAST_DECLINE();
             wa = (sp - 1) & 0xFFFF;
+            if (FAST) wt = mem_offset(MEM_WRAM + (wa & 0x1FFF));
             wv = gb_prmt(next_pc, 0, 0x4401);
             wn = 2;
             sp = (sp - 2) & 0xFFFF;
@@ -282,6 +345,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     case H_PUSH:
         if (FAST && !fast_stack_push(sp)) FAST_DECLINE();
         wa = (sp - 1) & 0xFFFF;
+        if (FAST) wt = mem_offset(MEM_WRAM + (wa & 0x1FFF));
         wv = gb_prmt(PAIR_OPERAND(), 0, 0x4401);
         wn = 2;
         sp = (sp - 2) & 0xFFFF;
@@ -290,25 +354,20 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         rv = v & (0xFF00u | op);
         sp = (sp + 2) & 0xFFFF;
         break;
-    case H_ROT: {
-        const uint32_t b = v & 0xFF, c = (f >> 4) & 1;
-        uint32_t cout, res;
-        switch (op & 7) {
-        case 0: cout = b >> 7; res = (b << 1) | cout; break;        // RLC
-        case 1: cout = b & 1; res = (b >> 1) | (cout << 7); break;  // RRC
-        case 2: cout = b >> 7; res = (b << 1) | c; break;           // RL
-        case 3: cout = b & 1; res = (b >> 1) | (c << 7); break;     // RR
-        case 4: cout = b >> 7; res = b << 1; break;                 // SLA
-        case 5: cout = b & 1; res = (b >> 1) | (b & 0x80); break;   // SRA
-        case 6: cout = 0; res = (b >> 4) | (b << 4); break;         // SWAP
-        default: cout = b & 1; res = b >> 1; break;                 // SRL
-        }
-        res &= 0xFF;
-        const uint32_t nf = ((res == 0 && !(op & 8)) ? FLAG_Z : 0) | (cout ? FLAG_C : 0);  // RLCA..RRA clear Z
+    case H_ROT: {  // branch-free: `ex` says where the shifted-in bit comes from (pd_rot_ex)
+        const uint32_t b = v & 0xFF, c = (f >> 4) & 1, right = ex & 1, b7 = b >> 7;
+        uint32_t cout = right ? (b & 1) : b7;
+        const uint32_t in = (((ex >> 1) & cout) | ((ex >> 2) & c) | ((ex >> 3) & b7)) & 1;
+        uint32_t res = right ? ((b >> 1) | (in << 7)) : (((b << 1) | in) & 0xFF);
+        if (ex & 0x10) { res = ((b >> 4) | (b << 4)) & 0xFF; cout = 0; }  // SWAP
+        const uint32_t nf = ((res == 0 && !(op & 8)) ? FLAG_Z : 0) | (cout << 4);  // RLCA..RRA clear Z
         rv = res | (nf << 8);
         wv = res;
         break;
     }
+    case H_CPL: rv = (~(hlaf >> 16) & 0xFF) | ((f | FLAG_N | FLAG_H) << 8); break;
+    case H_IME: m.ime = op; break;
+    case H_JPHL: next_pc = hlaf & 0xFFFF; break;
     case H_BIT: rv = ((f & FLAG_C) | FLAG_H | ((v & imm16 & 0xFF) ? 0 : FLAG_Z)) << 8; break;
     case H_RESSET:
         rv = (v & imm16 & 0xFF) | (imm16 >> 8);
@@ -388,12 +447,11 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     // at wa, then high byte at wa + 1 (LD (nn),SP)
     if (wn) {
         if (FAST) {
-            if (wn == 2) {  // push: both bytes in work RAM (checked by the handler); an odd address keeps them in one word
-                const uint32_t k1 = mem_offset(MEM_WRAM + (wa & 0x1FFF)), k2 = mem_offset(MEM_WRAM + ((wa - 1) & 0x1FFF));
-                memb[k1] = (uint8_t)wv;
-                memb[k2] = (uint8_t)(wv >> 8);
-            } else if (wt < FAST_WR_BANK) {
+            if (wt < FAST_WR_P1) {  // plain RAM; a push (both bytes in work RAM, checked by the handler) adds its high byte below
                 memb[wt] = (uint8_t)wv;
+                if (wn == 2) memb[mem_offset(MEM_WRAM + ((wa - 1) & 0x1FFF))] = (uint8_t)(wv >> 8);
+            } else if (wt == FAST_WR_P1) {  // joypad matrix select (a game's input routine writes it several times a frame)
+                memb[mem_offset(MEM_HI + 0x100)] = (uint8_t)joypad_pull(m, wv & 0xFF);
             } else if (wt == FAST_WR_BANK) {  // MBC3 ROM bank select (constant traffic in banked games)
                 uint32_t bank = wv & 0x7F;
                 bank = bank ? bank : 1;
@@ -406,6 +464,109 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
             for (uint32_t i = 0; i < count; i++) bus_write_full(m, i ? second : wa, (i ? wv >> 8 : wv) & 0xFF);
         }
     }
+    return true;
+}
+
+// The fast body of the lock-step build (k_run_frames, several envs per warp) as ONE straight line of code: no handler
+// dispatch at all.  Every lane computes the result of every kind of instruction the fast set knows -- the adder, the logic
+// unit, the rotator, BIT / RES / SET, CPL, the 16-bit increments and ADD HL, POP's mask, the branch condition -- from its own
+// control word, and selects pick what is written back; loads and stores are predicated.  A warp whose lanes are at
+// different instructions (the normal state of affairs: its envs are at different places of the game) therefore issues the
+// same instruction stream as a warp in lock-step; what it costs is the longest dependency chain (descriptor -> operand ->
+// ALU -> write-back), not the sum of the handlers its lanes happen to need.  Returns false, having changed nothing, for
+// whatever is outside the fast set (cpu_tick_slow redoes the tick).
+__device__ __forceinline__ bool cpu_exec_lockstep(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &cyc, uint8_t *memb, const uint8_t *rom,
+                                                  uint32_t bank_mask, bool declined) {
+    const uint32_t bcde = r.bcde, hlaf = r.hlaf, sp = r.sp;
+    const uint32_t w = d.w, h = d.x & 0xFF, op = gb_prmt(d.x, 0, 0x4441), ex = gb_prmt(d.x, 0, 0x4442), imm16 = d.y & 0xFFFFu, fall = d.y >> 16;
+    const uint32_t f = hlaf >> 24, a8 = (hlaf >> 16) & 0xFF, hl = hlaf & 0xFFFF;
+    declined |= h >= H_RARE;
+    // ---- control: the branch condition (mask in op, expected flag value in ex; unconditional: mask 0)
+    const bool cond = ((f ^ ex) & op) == 0;
+    const bool is_call = h == H_CALL, is_ret = h == H_RET, is_push = h == H_PUSH, is_pop = h == H_POP;
+    const bool jumps = cond && ((w & PDF_JUMP) || is_call), returns = cond && is_ret, pushes = (cond && is_call) || is_push;
+    // ---- operand and address
+    uint32_t v = gb_prmt(bcde, hlaf, w);  // byte 0 = source register
+    v = (w & PDF_IMM) ? imm16 : v;
+    const uint32_t pair = gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu;
+    uint32_t wa = (w & PDF_AIMM) ? imm16 : pair;
+    wa = (w & PDF_ASP) ? sp : wa;
+    wa = pushes ? ((sp - 1) & 0xFFFF) : wa;
+    uint32_t off;
+    const bool plain = fast_plain_offset(wa, off);
+    const bool rd = (w & PDF_RD) != 0, rd16 = (w & PDF_RD16) != 0, wr = (w & PDF_WR) != 0;
+    // stores outside plain RAM: MBC3 bank select, sound registers (dropped), P1; anything else is not for the fast body
+    const bool wr_special = wr && !plain;
+    const uint32_t wt = (wa - 0x2000u < 0x2000u) ? FAST_WR_BANK : (wa - 0xFF10u < 0x30u) ? FAST_WR_DROP : wa == 0xFF00u ? FAST_WR_P1 : FAST_WR_NONE;
+    declined |= wr_special && wt == FAST_WR_NONE;
+    declined |= pushes && !fast_stack_push(sp);
+    // loads: first byte from plain RAM, ROM or P1 / SB / SC; the second byte of POP / RET (always at SP + 1) from work RAM
+    const bool in_rom = wa < 0x8000u, rd_ok = plain || in_rom || (wa - 0xFF00u < 4u), rd16_ok = sp - 0xC000u < 0x3DFFu;
+    declined |= (rd && !rd_ok) || (rd16 && !rd16_ok);
+    v = fast_load_u8(in_rom ? rom : memb, in_rom ? wa + (wa >> 14) * rom_off : off, rd && rd_ok, v);
+    v |= fast_load_u8(memb, mem_offset(MEM_WRAM + ((sp + 1) & 0x1FFF)), rd16 && rd16_ok, 0) << 8;
+    const uint32_t b = v & 0xFF, b7 = b >> 7;
+    // ---- every unit computes
+    // adder.  INC / DEC: a = v, x = +1 / -1, C kept, ex = 0 / N|H;  ADD ADC SUB SBC CP: a = A, x = v or its complement (ex = 0 / 0xFF)
+    const bool inc = (w & PDF_INCDEC) != 0;
+    const uint32_t ad_a = inc ? b : a8, ad_x = inc ? op : (b ^ ex), ad_c = inc ? 0u : ((((f >> 4) & op) ^ ex) & 1);
+    const uint32_t sum = ad_a + ad_x + ad_c, ad_res = sum & 0xFF;
+    const uint32_t ad_f = ((((ad_a ^ ad_x ^ sum) & 0x10) << 1) ^ (ex & 0x60)) | (inc ? (f & FLAG_C) : (((sum >> 4) ^ ex) & 0x10)) | (ad_res == 0 ? FLAG_Z : 0);
+    // logic: AND a & v; XOR a ^ v; OR (a & v) | (a ^ v)
+    const uint32_t lg_res = ((a8 & b) & ex) | ((a8 ^ b) & op);
+    const uint32_t lg_f = (op ? 0 : FLAG_H) | (lg_res == 0 ? FLAG_Z : 0);
+    // rotates and shifts (pd_rot_ex)
+    const uint32_t right = ex & 1;
+    uint32_t rt_c = right ? (b & 1) : b7;
+    const uint32_t rt_in = (((ex >> 1) & rt_c) | ((ex >> 2) & (f >> 4)) | ((ex >> 3) & b7)) & 1;
+    uint32_t rt_res = right ? ((b >> 1) | (rt_in << 7)) : (((b << 1) | rt_in) & 0xFF);
+    rt_res = (ex & 0x10) ? (((b >> 4) | (b << 4)) & 0xFF) : rt_res;
+    rt_c = (ex & 0x10) ? 0u : rt_c;
+    const uint32_t rt_f = ((rt_res == 0 && !(op & 8)) ? FLAG_Z : 0) | (rt_c << 4);
+    // 16-bit: INC rr / DEC rr / HL+ / HL- and ADD HL,rr
+    const uint32_t hli = ((pair + gb_prmt(d.x, 0, 0x9991)) & 0xFFFFu) | (v << 16);
+    const uint32_t t16 = hl + pair;
+    const uint32_t addhl = (t16 & 0xFFFF) | (((f & FLAG_Z) | (((hl & 0xFFF) + (pair & 0xFFF)) > 0xFFF ? FLAG_H : 0) | (t16 > 0xFFFF ? FLAG_C : 0)) << 24);
+    // ---- select the result: 8-bit results travel as res | new F << 8 (the write-back selectors say what is kept)
+    uint32_t rv = v;
+    rv = (w & (PDF_INCDEC | PDF_ARITH)) ? (ad_res | (ad_f << 8)) : rv;
+    rv = h == H_LOGIC ? (lg_res | (lg_f << 8)) : rv;
+    rv = h == H_ROT ? (rt_res | (rt_f << 8)) : rv;
+    rv = h == H_BIT ? (((f & FLAG_C) | FLAG_H | ((b & imm16) ? 0 : FLAG_Z)) << 8) : rv;
+    rv = h == H_RESSET ? ((b & imm16) | (imm16 >> 8)) : rv;
+    rv = h == H_CPL ? ((~a8 & 0xFF) | ((f | FLAG_N | FLAG_H) << 8)) : rv;
+    rv = h == H_HLI ? hli : rv;
+    rv = h == H_ADD_HL ? addhl : rv;
+    rv = is_pop ? (v & (0xFF00u | op)) : rv;
+    // ---- next PC, stack pointer, cycles
+    uint32_t next_pc = jumps ? imm16 : fall;
+    next_pc = returns ? (v & 0xFFFF) : next_pc;
+    next_pc = h == H_JPHL ? hl : next_pc;
+    cyc = (d.x >> 24) + ((jumps || returns) ? (ex & 0xF) : 0u);
+    const uint32_t new_sp = (sp + ((is_pop || returns) ? 2u : 0u) - (pushes ? 2u : 0u)) & 0xFFFF;
+    // ---- what a store writes: the unit's 8-bit result (the register itself for LD (HL+-),A); a push the pair or the return
+    // address, high byte first
+    uint32_t wv = h == H_HLI ? v : rv;
+    wv = pushes ? gb_prmt(is_push ? pair : fall, 0, 0x4401) : wv;
+    if (declined) return false;  // nothing has been changed
+    r.bcde = gb_prmt(bcde, rv, d.z);
+    r.hlaf = gb_prmt(hlaf, rv, d.z >> 16);
+    r.sp = new_sp;
+    r.pc = next_pc;
+    if ((wr && plain) || pushes) memb[off] = (uint8_t)wv;
+    if (pushes) memb[mem_offset(MEM_WRAM + ((sp - 2) & 0x1FFF))] = (uint8_t)(wv >> 8);
+    if (wr_special) {
+        if (wt == FAST_WR_P1) {  // joypad matrix select (a game's input routine writes it several times a frame)
+            memb[mem_offset(MEM_HI + 0x100)] = (uint8_t)joypad_pull(m, wv & 0xFF);
+        } else if (wt == FAST_WR_BANK) {  // MBC3 ROM bank select (constant traffic in banked games)
+            uint32_t bank = wv & 0x7F;
+            bank = bank ? bank : 1;
+            m.rombank = bank;
+            rom_off = (bank_mask ? (bank & bank_mask) : (bank % m.rom_banks)) * 0x4000u - 0x4000u;
+            m.rom_off = rom_off;
+        }
+    }
+    if ((w & PDF_RETI) || h == H_IME) m.ime = h == H_IME ? op : 1u;
     return true;
 }
 
@@ -478,7 +639,15 @@ again:
                 if (!SIMT) break;
                 leave = true;
             }
+#if defined(GB_OPT_NO_LOCKSTEP)
             if (!cpu_exec<true, SIMT>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
+#else
+            if (SIMT) {
+                if (!cpu_exec_lockstep(m, d, r, rom_off, cyc, memb, rom, cx.bank_mask, leave)) break;
+            } else {
+                if (!cpu_exec<true, false>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
+            }
+#endif
             GB_TRACE_SLOT(0, pc < 0x8000u ? pc + (pc >> 14) * rom_off : (0xF00000u | pc), d.x, d.w);
             n_instr++;
             rem -= (int)cyc;

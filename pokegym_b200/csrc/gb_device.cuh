@@ -236,6 +236,24 @@ __device__ __forceinline__ uint32_t apply_palette(uint32_t idx, uint32_t pal) {
     return s;
 }
 
+// RENDER_BATCH tiles of map row `row` (offset inside VRAM) from column `col` on (wrapping at 32), tile row `fine_y`:
+// colour indices of their 8 pixels each.  All map bytes are loaded before the first tile row, all tile rows before the
+// first use, so a batch costs two memory round trips; a batch may run past the last tile the caller needs (the
+// addresses stay inside VRAM).
+#define RENDER_BATCH 7
+__device__ __forceinline__ void render_fetch_tiles(const Machine &m, uint32_t row, uint32_t col, uint32_t fine_y, uint32_t tds, uint32_t (&px)[RENDER_BATCH]) {
+    uint32_t t[RENDER_BATCH];
+#pragma unroll
+    for (int j = 0; j < RENDER_BATCH; j++) t[j] = mem_rd(m, MEM_VRAM + row + ((col + j) & 31));
+#pragma unroll
+    for (int j = 0; j < RENDER_BATCH; j++) {
+        const uint32_t tt = tds ? t[j] : (t[j] ^ 0x80) + 128;
+        px[j] = vram_rd16(m, MEM_VRAM + tt * 16 + fine_y * 2);
+    }
+#pragma unroll
+    for (int j = 0; j < RENDER_BATCH; j++) px[j] = tile_row_indices(px[j]);
+}
+
 // Renderer.scanline + Renderer.scanline_sprites for line y.  `line` is this thread's 10-word
 // scratch in shared memory (stride `ls` words), `keys` its 10-entry sprite sort scratch.
 __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint32_t *keys, uint32_t ls) {
@@ -248,6 +266,8 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
     const int wstart = win_line ? (wx > 0 ? wx : 0) : 160;  // first screen x covered by the window
 
     // ---- background layer, x in [0, wstart)
+    // Tiles are fetched seven at a time (render_fetch_tiles): seven independent map-byte loads, then seven independent
+    // tile-row loads, so the two dependent VRAM accesses of a tile are paid once per batch, not once per tile.
     if (wstart > 0) {
         if (lcdc & 0x01) {
             const uint32_t map_base = (lcdc & 0x08) ? 0x1C00u : 0x1800u;
@@ -259,23 +279,23 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
             uint32_t out = 0;
             const uint32_t nwords = ((uint32_t)wstart + 15) >> 4;
             while (out < nwords) {
-                uint32_t t = mem_rd(m, MEM_VRAM + row + (col & 31));
-                col++;
-                if (!tds) t = (t ^ 0x80) + 128;
-                uint32_t rowdata = vram_rd16(m, MEM_VRAM + t * 16 + fine_y * 2);
-                uint32_t px = tile_row_indices(rowdata);  // colour indices; BGP is applied per word below
-                if (nbits < 0) {
-                    acc = (uint64_t)(px >> (uint32_t)(-nbits));
-                    nbits += 16;
-                } else {
-                    acc |= (uint64_t)px << nbits;
-                    nbits += 16;
-                }
-                if (nbits >= 32) {
-                    line[out * ls] = (uint32_t)acc;
-                    out++;
-                    acc >>= 32;
-                    nbits -= 32;
+                uint32_t px7[RENDER_BATCH];
+                render_fetch_tiles(m, row, col, fine_y, tds, px7);
+                col += RENDER_BATCH;
+#pragma unroll
+                for (int j = 0; j < RENDER_BATCH; j++) {
+                    if (out < nwords) {
+                        const uint32_t px = px7[j];
+                        if (nbits < 0) acc = (uint64_t)(px >> (uint32_t)(-nbits));
+                        else acc |= (uint64_t)px << nbits;
+                        nbits += 16;
+                        if (nbits >= 32) {
+                            line[out * ls] = (uint32_t)acc;
+                            out++;
+                            acc >>= 32;
+                            nbits -= 32;
+                        }
+                    }
                 }
             }
         } else {
@@ -296,25 +316,29 @@ __device__ inline void render_line(Machine &m, uint32_t y, uint32_t *line, uint3
         int nbits = (int)lead - (int)((first & 7) * 2);
         bool first_tile = true;
         while (out < FB_LINE_WORDS) {
-            uint32_t t = mem_rd(m, MEM_VRAM + row + (col & 31));
-            col++;
-            if (!tds) t = (t ^ 0x80) + 128;
-            uint32_t rowdata = vram_rd16(m, MEM_VRAM + t * 16 + fine_y * 2);
-            uint32_t px = tile_row_indices(rowdata);  // colour indices; BGP is applied per word below
-            if (first_tile) {
-                px >>= (first & 7) * 2;
-                acc |= (uint64_t)px << lead;
-                nbits = (int)lead + 16 - (int)((first & 7) * 2);
-                first_tile = false;
-            } else {
-                acc |= (uint64_t)px << nbits;
-                nbits += 16;
-            }
-            if (nbits >= 32) {
-                line[out * ls] = (uint32_t)acc;
-                out++;
-                acc >>= 32;
-                nbits -= 32;
+            uint32_t px7[RENDER_BATCH];
+            render_fetch_tiles(m, row, col, fine_y, tds, px7);
+            col += RENDER_BATCH;
+#pragma unroll
+            for (int j = 0; j < RENDER_BATCH; j++) {
+                if (out < FB_LINE_WORDS) {
+                    uint32_t px = px7[j];
+                    if (first_tile) {
+                        px >>= (first & 7) * 2;
+                        acc |= (uint64_t)px << lead;
+                        nbits = (int)lead + 16 - (int)((first & 7) * 2);
+                        first_tile = false;
+                    } else {
+                        acc |= (uint64_t)px << nbits;
+                        nbits += 16;
+                    }
+                    if (nbits >= 32) {
+                        line[out * ls] = (uint32_t)acc;
+                        out++;
+                        acc >>= 32;
+                        nbits -= 32;
+                    }
+                }
             }
         }
     }

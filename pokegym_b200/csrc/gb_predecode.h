@@ -16,6 +16,7 @@
 //        cycles  T-cycles (condition false / unconditional)
 //        ex      low nibble: extra T-cycles when a conditional branch is taken; bits 4 / 7: flag value the
 //                condition expects (compared under the mask in `op`)
+//        (H_ROT: ex = pd_rot_ex of the rotate kind)
 //        op      handler operand: ALU op, INC/DEC select, signed +-1 for HL+/HL-/INC rr/DEC rr, condition mask
 //                (0 = always, 0x80 = Z, 0x10 = C), rotate kind, POP low-byte mask, or the opcode (H_RARE)
 //   y: imm16 | next_pc << 16      imm16: immediate, or a ready-made value -- the JR/JP/CALL/RST target, 0xFF00|n
@@ -49,6 +50,9 @@ enum {
     H_ROT,       // CB rotates / shifts / SWAP on v, and RLCA RRCA RLA RRA (op bit 3: Z forced clear)
     H_BIT,       // BIT b,v
     H_RESSET,    // RES / SET b,v
+    H_CPL,       // CPL
+    H_IME,       // DI / EI (op = the new IME; PyBoy: EI takes effect at once)
+    H_JPHL,      // JP HL
     H_RARE,      // everything else, by opcode (never executed by the fast loop)
     H_SLOW,      // not pre-decodable here (instruction straddles a bank boundary): decoded on the fly by the slow tick
     H__COUNT
@@ -122,6 +126,13 @@ static inline void pd_b_cond(pd_builder *b, uint32_t cc, uint32_t taken_extra) {
     uint32_t mask = (cc & 2) ? 0x10u : 0x80u;
     b->op = mask;
     b->ex = taken_extra | ((cc & 1) ? mask : 0u);
+}
+
+// rotate / shift kind y = RLC RRC RL RR SLA SRA SWAP SRL -> `ex` of H_ROT: bit 0 shifts right, bits 1 / 2 / 3 shift in the
+// bit that falls out / the carry flag / bit 7 (SRA), bit 4 swaps the nibbles instead
+static inline uint32_t pd_rot_ex(uint32_t y) {
+    static const uint32_t t[8] = {0x02, 0x03, 0x04, 0x05, 0x00, 0x09, 0x10, 0x01};
+    return t[y & 7];
 }
 
 // ALU group y = ADD ADC SUB SBC AND XOR OR CP
@@ -232,10 +243,14 @@ static inline void pd_build_base(pd_desc_t *t) {
             default:
                 if (y < 4) {  // RLCA RRCA RLA RRA: the CB rotate of A with Z forced clear
                     pd_b_init(&b, H_ROT, 1, 4);
-                    b.op = y | 8u; b.srcsel = 6;
+                    b.op = y | 8u; b.ex = pd_rot_ex(y); b.srcsel = 6;
                     pd_b_write(&b, 6, 0); pd_b_write(&b, 7, 1);
                 }
-                break;  // DAA CPL SCF CCF: rare
+                else if (y == 5) {  // CPL
+                    pd_b_init(&b, H_CPL, 1, 4);
+                    pd_b_write(&b, 6, 0); pd_b_write(&b, 7, 1);
+                }
+                break;  // DAA SCF CCF: rare
             }
         } else {
             switch (z) {
@@ -265,8 +280,10 @@ static inline void pd_build_base(pd_desc_t *t) {
                     b.flags |= PDF_RD | PDF_RD16 | PDF_ASP | (p == 1 ? PDF_RETI : 0);
                 } else if (p == 3) {
                     b.cyc = 8;  // LD SP,HL (rare)
+                } else {
+                    pd_b_init(&b, H_JPHL, 1, 4);
                 }
-                break;  // JP HL: rare, 4 cycles
+                break;
             case 2:
                 if (y < 4) {
                     pd_b_init(&b, H_JUMP, 3, 12);
@@ -283,7 +300,8 @@ static inline void pd_build_base(pd_desc_t *t) {
                 break;
             case 3:
                 if (y == 0) { pd_b_init(&b, H_JUMP, 3, 16); b.kind = PDK_IMM16; }
-                break;  // CB prefix (own page), DI, EI, illegal: rare
+                else if (y == 6 || y == 7) { pd_b_init(&b, H_IME, 1, 4); b.op = y & 1; }  // DI / EI
+                break;  // CB prefix (own page), illegal: rare
             case 4:
                 if (y < 4) {
                     pd_b_init(&b, H_CALL, 3, 12);
@@ -323,7 +341,7 @@ static inline void pd_build_base(pd_desc_t *t) {
         if (z == 6) b.flags |= PDF_RD | (x == 1 ? 0 : PDF_WR);
         else pd_b_src_reg(&b, z);
         if (x == 0) {
-            b.op = y;
+            b.op = y; b.ex = pd_rot_ex(y);
             pd_b_write(&b, 7, 1);
         } else if (x == 1) {
             b.imm = 1u << y;
