@@ -70,6 +70,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--preroll", type=int, default=PREROLL)
+    ap.add_argument("--groups", type=int, default=0,
+                    help="env groups stepping on separate CUDA streams (pokegym_b200.EnvGroups); 0 = 2 while every env has a warp of its own, else 1")
     ap.add_argument("--legs", default="all", help="'all', 'none' or a comma list of leg names (1 GPU only)")
     ap.add_argument("--only-leg", default=None, help="run one leg alone and print its record (profiling)")
     ap.add_argument("--config", default=None, choices=[None, "single"], help="single: BASELINE.json config 1, the protocol of the reference's test.py")
@@ -307,43 +309,49 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU legs
 
-def e2e_host_loop(h, E, n_e2e, world=1, dev=None):
+def e2e_host_loop(hs, E, n_e2e, world=1, dev=None):
     """The same metric through gbenv_submit_host / gbenv_fetch_host with pinned host buffers: actions H2D and obs / reward / done
     D2H inside the timed region, step t+1 submitted before the results of step t are fetched (two steps in flight), so the
     observation copy overlaps the next emulation kernel -- what a vectoriser that keeps two rollout slots in flight does.
+    `hs`: the handles of the env groups (one, or several that share the E envs evenly).
     Returns env-steps/s of this rank's E envs (wall clock around the loop, max over ranks when world > 1)."""
     import torch
     import torch.distributed as dist
 
     from pokegym_b200 import _capi
+    from pokegym_b200.dist import max_over_ranks
 
+    hs = list(hs) if isinstance(hs, (list, tuple)) else [hs]
+    G, n = len(hs), E // len(hs)
     act_h = torch.randint(0, 8, (n_e2e + 4, E), dtype=torch.uint8).pin_memory()
     obs_h = [torch.zeros((E, _capi.OBS_BYTES), dtype=torch.uint8).pin_memory() for _ in range(2)]
     rew_h = [torch.zeros(E, dtype=torch.float64).pin_memory() for _ in range(2)]
     done_h = [torch.zeros(E, dtype=torch.uint8).pin_memory() for _ in range(2)]
 
     def submit(i):
-        h.submit_host(act_h[i].numpy(), obs_h[i % 2].numpy(), rew_h[i % 2].numpy(), done_h[i % 2].numpy())
+        for g, h in enumerate(hs):
+            a, b = g * n, (g + 1) * n
+            h.submit_host(act_h[i][a:b].numpy(), obs_h[i % 2][a:b].numpy(), rew_h[i % 2][a:b].numpy(), done_h[i % 2][a:b].numpy())
+
+    def fetch():
+        for h in hs:
+            h.fetch_host()
 
     for i in range(3):
         submit(i)
-        h.fetch_host()
+        fetch()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     submit(3)
     for i in range(4, 3 + n_e2e):
-        submit(i)        # step i queued behind step i-1 ...
-        h.fetch_host()   # ... while the results of step i-1 arrive (blocks until they are in the host buffers)
+        submit(i)  # step i queued behind step i-1 ...
+        fetch()    # ... while the results of step i-1 arrive (blocks until they are in the host buffers)
         float(rew_h[(i - 1) % 2][0])  # the caller reads them
-    h.fetch_host()
+    fetch()
     float(rew_h[(2 + n_e2e) % 2][0])
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     return world * E * n_e2e / e2e_s
 
 
@@ -450,6 +458,8 @@ def main():
 
     import __graft_entry__ as g
     from pokegym_b200 import _capi
+    from pokegym_b200.dist import all_reduce_info, max_over_ranks
+    from pokegym_b200.groups import EnvGroups
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -477,8 +487,13 @@ def main():
         return
     E, K, W = args.envs_per_gpu, args.steps, max(args.warmup, 3)
     rom = build_rom(args.rom)
-    h = _capi.Handle(lib, E, rom, device_id=local_rank)
-    start_envs(h, args.state, E)  # every env starts from the same state and diverges through its actions
+    props = torch.cuda.get_device_properties(dev)
+    # Env groups (pokegym_b200.EnvGroups): while every env has a warp of its own (the emulation kernel is then bound by
+    # instruction issue) the batch steps as two groups on two streams, so that the tail of one group's launch -- its few
+    # slowest envs -- is filled by the other group; bigger batches are latency bound and gain nothing from it.
+    G = args.groups if args.groups > 0 else (2 if E <= props.multi_processor_count * 32 and E % 64 == 0 else 1)
+    h = EnvGroups(lib, E, rom, n_groups=G, device_id=local_rank)
+    h.for_each(lambda hh, g, st: start_envs(hh, args.state, E // G))  # every env starts from the same state and diverges through its actions
     rollout = torch.zeros((ROLLOUT_T, E, _capi.OBS_BYTES), dtype=torch.uint8, device=dev)
     reward = torch.zeros((ROLLOUT_T, E), dtype=torch.float64, device=dev)
     done = torch.zeros((ROLLOUT_T, E), dtype=torch.uint8, device=dev)
@@ -487,14 +502,14 @@ def main():
     gen.manual_seed(1234 + rank)
     n_act = 512
     actions = torch.randint(0, 8, (n_act, E), generator=gen, device=dev, dtype=torch.uint8)
+    torch.cuda.synchronize()
     h.reset(rollout[0])
     reduces = 0
 
     def reduce_info():  # episode-info scalars summed over envs, then over ranks (the path's only collective)
         nonlocal reduces
-        h.reduce_info(info_sum)
-        if world > 1:
-            dist.all_reduce(info_sum)
+        h.reduce_info(info_sum)  # joins the groups: the rollout is complete here
+        all_reduce_info(info_sum)  # NCCL sum over ranks (a no-op for one rank)
         reduces += 1
 
     def step(i):
@@ -505,6 +520,7 @@ def main():
 
     for i in range(args.preroll + W):
         step(i)
+    h.join()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -522,6 +538,7 @@ def main():
         step(i)
     if reduces == 0:  # a short run ends inside a rollout: the reduction still belongs to the timed region
         reduce_info()
+    h.join()  # the timed region ends when every group has finished its last step
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -531,16 +548,14 @@ def main():
     k1b = h.kernel_time_total(1)
     if world > 1:
         dist.barrier()
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms, dev)
     value = world * E * K / (ms / 1000.0)
 
     # ---- end to end through the host-buffer entry points (pinned memory, copies inside the timed region).  Double
     # buffered: step t+1 is submitted before the results of step t are fetched, so the 94 MB D2H of the observations
     # overlaps the next emulation kernel -- what a vectoriser that keeps two rollout slots in flight does.
     n_e2e = max(3, min(args.e2e_steps, K))
-    e2e_value = e2e_host_loop(h, E, n_e2e, world, dev)
+    e2e_value = e2e_host_loop(h.handles, E, n_e2e, world, dev)
 
     if rank != 0:
         if world > 1:
@@ -550,33 +565,36 @@ def main():
     run_ms = (k0b[0] - k0[0]) / max(1, k0b[1] - k0[1])
     wrap_ms = (k1b[0] - k1[0]) / max(1, k1b[1] - k1[1])
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES_PER_ENV_STEP * E / (run_ms / 1000.0) / 1e9
+    achieved = ALGO_BYTES_PER_ENV_STEP * (E // G) / (run_ms / 1000.0) / 1e9  # one launch steps one group
     counters = recorded_counters()
     instr = c1.instructions - c0.instructions
-    props = torch.cuda.get_device_properties(dev)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     line = {
         "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args), "envs_per_gpu": E, "act_freq": 24, "rom": args.rom, "parallelism": f"env-sharded x{world}",
+                   "env_groups": G, "env_groups_note": (f"{G} groups of {E // G} envs step on {G} CUDA streams (pokegym_b200.EnvGroups); the single-group "
+                                                        "figure is legs.main_4096" if G > 1 else "one group"),
                    "preroll_steps": args.preroll, "info_allreduces_in_timed_region": reduces,
                    "l2_policy": f"working set {E * (16896 + 5760 + 23040 + 1152) / 1e6:.0f} MB of env state + obs per GPU exceeds the 126 MB L2; no explicit flush"},
         "frames_per_s": 24 * value,
         "emulated_instr_per_s": instr / (ms / 1000.0) * world,
         "roofline": {"bound": "hbm", "kernel": "k_run_frames", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (counters or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                     "kernel_ms": run_ms, "kernel_share_of_step": run_ms / (ms / K), "wrap_kernels_ms": wrap_ms,
-                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * E,
-                     "note": "the HBM figure is the prescribed one; the kernel is an interpreter and is bounded by instruction issue, see `issue`"},
+                     "kernel_ms": run_ms, "launches_per_step": G, "envs_per_launch": E // G,
+                     "kernel_share_of_step": run_ms / (ms / K) if G == 1 else None, "wrap_kernels_ms": wrap_ms,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * (E // G),
+                     "note": "the HBM figure is the prescribed one; the kernel is an interpreter and is bounded by instruction issue, see `issue`"
+                             + ("; the launches of the env groups overlap, so kernel_ms is the duration of one group's launch while the other group's runs beside it" if G > 1 else "")},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": E, "d2h_bytes_per_step": E * (_capi.OBS_BYTES + 8 + 1),
                 "steps": n_e2e, "api": "gbenv_submit_host / gbenv_fetch_host (pinned host buffers, two steps in flight)"},
         "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
         "clocks": clocks,
         "faults": int(c1.faults),
     }
-    if counters and counters.get("envs_per_launch") == E:
-        line["issue"] = issue_record(counters, run_ms, sm_mhz, props.multi_processor_count)
-    want = [] if args.legs == "none" else ([x for x in LEGS if x != "main_4096"] if args.legs == "all" else [x for x in args.legs.split(",") if x in LEGS])
+    if counters and counters.get("envs_per_launch") == E // G:
+        line["issue"] = issue_record(counters, run_ms / G, sm_mhz, props.multi_processor_count)  # G launches share the machine
+    want = [] if args.legs == "none" else ([x for x in LEGS if G > 1 or x != "main_4096"] if args.legs == "all" else [x for x in args.legs.split(",") if x in LEGS])
     if world == 1 and want:
         h.close()
         del rollout

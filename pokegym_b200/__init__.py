@@ -12,4 +12,8 @@ def __getattr__(name):
         from . import vec_env
 
         return getattr(vec_env, name)
+    if name == "EnvGroups":
+        from . import groups
+
+        return groups.EnvGroups
     raise AttributeError(name)

@@ -206,3 +206,55 @@ def test_error_paths_and_limits(cuda_lib, roms, monkeypatch):
     assert s.counters().faults == 1
     with pytest.raises(_capi.GbEnvError, match="exploration map"):
         s.counts_map(0)
+
+
+def test_env_groups_match_one_handle_and_the_oracle(cuda_lib, oracle_lib, roms):
+    """pokegym_b200.EnvGroups: the batch held as two handles stepping on two CUDA streams.  Env i of the batch is env
+    i - g * n of group g, so observations, rewards, dones and the reduced info vector must equal the oracle's for one
+    batch of the same size, step by step, including a masked reset in the middle."""
+    import torch
+
+    from pokegym_b200 import EnvGroups, _capi
+
+    E, G = 128, 2
+    rom = roms("pokelike")
+    groups = EnvGroups(cuda_lib, E, rom, n_groups=G)
+    groups.for_each(lambda h, g, st: h.tick(60, True, stream=st))
+    cpu = _capi.Handle(oracle_lib, E, rom)
+    cpu.tick(60, True)
+    dev = groups.device
+    obs = torch.zeros((E, _capi.OBS_BYTES), dtype=torch.uint8, device=dev)
+    rew = torch.zeros(E, dtype=torch.float64, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev)
+    oc, rc, dc = np.zeros((E, _capi.OBS_BYTES), np.uint8), np.zeros(E), np.zeros(E, np.uint8)
+    groups.reset(obs, max_episode_steps=6)
+    cpu.reset(oc, max_episode_steps=6)
+    torch.cuda.synchronize()
+    assert np.array_equal(obs.cpu().numpy(), oc)
+    rng = np.random.default_rng(21)
+    for t in range(9):
+        act = rng.integers(0, 8, E).astype(np.uint8)
+        groups.step(torch.from_numpy(act).to(dev), obs, rew, done)  # returns with both groups still running
+        groups.join()
+        cpu.step(act, oc, rc, dc)
+        torch.cuda.synchronize()
+        assert np.array_equal(rew.cpu().numpy(), rc), t
+        assert np.array_equal(done.cpu().numpy(), dc), t
+        assert np.array_equal(obs.cpu().numpy(), oc), t
+        if dc.any():
+            groups.reset(obs, mask=done.clone(), max_episode_steps=6)
+            cpu.reset(oc, mask=dc.copy(), max_episode_steps=6)
+            torch.cuda.synchronize()
+            assert np.array_equal(obs.cpu().numpy(), oc), t
+    s_g = torch.zeros(_capi.INFO_SCALARS, dtype=torch.float64, device=dev)
+    groups.reduce_info(s_g)
+    s_c = np.zeros(_capi.INFO_SCALARS)
+    cpu.reduce_info(s_c)
+    torch.cuda.synchronize()
+    assert np.allclose(s_g.cpu().numpy(), s_c, rtol=1e-12, atol=0)  # partial sums per group: the association differs
+    assert groups.counters().instructions == cpu.counters().instructions
+    for e in (0, E // G - 1, E // G, E - 1):
+        assert groups.handles[e // (E // G)].save_state(e % (E // G)) == cpu.save_state(e)
+    groups.close()
+    with pytest.raises(ValueError):
+        EnvGroups(cuda_lib, 100, rom, n_groups=3)
