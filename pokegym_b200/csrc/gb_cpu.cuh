@@ -40,6 +40,7 @@ __constant__ uint4 c_base_desc[512];  // per-opcode base descriptors (pd_build_b
 
 #define MODE_ATTN 0x8000u   // pending interrupt / HALT / PyBoy's interrupt_queued latch: the tick starts in cpu_attention
 #define MODE_POST 0x10000u  // HALT: the tick ends in cpu_post_slow
+#define MODE_DEFER 0x20000u  // deferred PPU: a line of this frame is recorded -- VRAM / OAM stores go through the slow tick (render_flush)
 
 struct RunCtx {  // uniform per launch
     const uint4 *rom_dec;
@@ -48,7 +49,7 @@ struct RunCtx {  // uniform per launch
 
 __device__ __forceinline__ uint32_t hot_mode(const Machine &m) {
     const uint32_t attn = m.halted | m.iq | (m.iflag & m.ie & 0x1F), post = m.halted;
-    return (attn ? MODE_ATTN : 0u) | (post ? MODE_POST : 0u);
+    return (attn ? MODE_ATTN : 0u) | (post ? MODE_POST : 0u) | (m.defer_active ? MODE_DEFER : 0u);
 }
 #define TIMA_ON 0x04000000u  // TAC bit 2 inside Machine.tmr
 // Cycles until the interpreter has to stop: for the LCD (the next hard event, see lcd_deadline) or, while TIMA runs, for the
@@ -243,6 +244,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
             if (w & PDF_WR) {
                 wt = plain ? off : (wa - 0x2000u < 0x2000u) ? FAST_WR_BANK : (wa - 0xFF10u < 0x30u) ? FAST_WR_DROP : wa == 0xFF00u ? FAST_WR_P1 : FAST_WR_NONE;
                 if (wt == FAST_WR_NONE) FAST_DECLINE();
+                if ((mode & MODE_DEFER) && (wa - 0x8000u < 0x2000u || wa - 0xFE00u < 0x100u)) FAST_DECLINE();  // render_flush first
             }
             if (w & PDF_RD) {
                 // P1 (the byte Interaction.pull left there), SB, SC and 0xFF03 read back from the IO array like plain RAM
@@ -261,6 +263,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
             if (FAST && (w & PDF_WR)) {
                 wt = fast_store_target(wa);
                 if (wt == FAST_WR_NONE) FAST_DECLINE();
+                if ((mode & MODE_DEFER) && (wa - 0x8000u < 0x2000u || wa - 0xFE00u < 0x100u)) FAST_DECLINE();  // render_flush first
             }
             if (w & PDF_RD) {
                 v = rd8(wa);
@@ -475,8 +478,8 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
 // same instruction stream as a warp in lock-step; what it costs is the longest dependency chain (descriptor -> operand ->
 // ALU -> write-back), not the sum of the handlers its lanes happen to need.  Returns false, having changed nothing, for
 // whatever is outside the fast set (cpu_tick_slow redoes the tick).
-__device__ __forceinline__ bool cpu_exec_lockstep(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &cyc, uint8_t *memb, const uint8_t *rom,
-                                                  uint32_t bank_mask, bool declined) {
+__device__ __forceinline__ bool cpu_exec_lockstep(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t mode, uint32_t &cyc, uint8_t *memb,
+                                                  const uint8_t *rom, uint32_t bank_mask, bool declined) {
     const uint32_t bcde = r.bcde, hlaf = r.hlaf, sp = r.sp;
     const uint32_t w = d.w, h = d.x & 0xFF, op = gb_prmt(d.x, 0, 0x4441), ex = gb_prmt(d.x, 0, 0x4442), imm16 = d.y & 0xFFFFu, fall = d.y >> 16;
     const uint32_t f = hlaf >> 24, a8 = (hlaf >> 16) & 0xFF, hl = hlaf & 0xFFFF;
@@ -500,6 +503,7 @@ __device__ __forceinline__ bool cpu_exec_lockstep(Machine &m, const uint4 d, Cpu
     const uint32_t wt = (wa - 0x2000u < 0x2000u) ? FAST_WR_BANK : (wa - 0xFF10u < 0x30u) ? FAST_WR_DROP : wa == 0xFF00u ? FAST_WR_P1 : FAST_WR_NONE;
     declined |= wr_special && wt == FAST_WR_NONE;
     declined |= pushes && !fast_stack_push(sp);
+    declined |= wr && (mode & MODE_DEFER) && (wa - 0x8000u < 0x2000u || wa - 0xFE00u < 0x100u);  // deferred PPU: render_flush first
     // loads: first byte from plain RAM, ROM or P1 / SB / SC; the second byte of POP / RET (always at SP + 1) from work RAM
     const bool in_rom = wa < 0x8000u, rd_ok = plain || in_rom || (wa - 0xFF00u < 4u), rd16_ok = sp - 0xC000u < 0x3DFFu;
     declined |= (rd && !rd_ok) || (rd16 && !rd16_ok);
@@ -643,7 +647,7 @@ again:
             if (!cpu_exec<true, SIMT>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
 #else
             if (SIMT) {
-                if (!cpu_exec_lockstep(m, d, r, rom_off, cyc, memb, rom, cx.bank_mask, leave)) break;
+                if (!cpu_exec_lockstep(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
             } else {
                 if (!cpu_exec<true, false>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
             }

@@ -60,6 +60,10 @@ struct Machine {
     // statistics (n_cycles = clock delta + cyc_adj, see machine_store)
     uint32_t n_instr, n_cycles, cyc_adj, clock0;
     uint32_t lazy;  // k_run_frames: soft LCD events may be applied late (set by lcd_deadline)
+    // deferred PPU: lines [defer_from, defer_next) of the rendered frame are recorded in `dl` and not yet drawn; defer_active:
+    // a line of the current frame has been recorded (from then on VRAM / OAM writes leave the fast loop and flush first)
+    uint32_t defer_from, defer_next, defer_active;
+    uint32_t *dl;  // this env's deferred-line records (word k of line y at dl[(y * 3 + k) * 32]), or null: render at once
     int t_sync;  // k_run_frames: value of the interpreter's cycle countdown when clock / divc were last brought up to date
     // memory (pointers already offset to this env's lane inside its tile)
     uint8_t *memb;   // plain RAM, byte i at memb[((i >> 2) << 7) | (i & 3)]
@@ -82,6 +86,7 @@ __device__ __forceinline__ void machine_bind(Machine &m, const DevArrays &d, int
     m.lp = (uint2 *)(d.lp + (size_t)tile * LP_WORDS * GB_TILE) + lane;
     m.rom = d.rom;
     m.rom_banks = d.rom_banks;
+    m.dl = nullptr;  // the emulation kernel switches deferred rendering on (RunParams.defer)
 }
 
 __device__ __forceinline__ void machine_set_rombank(Machine &m, uint32_t bank) {
@@ -120,7 +125,9 @@ __device__ inline void machine_load(Machine &m, const DevArrays &d, int tile, in
     w = r[R_JOY * 32];
     m.joy_dir = w & 0xFF; m.joy_std = (w >> 8) & 0xFF; m.ly_window = (int)(int8_t)((w >> 16) & 0xFF); m.lp_dirty = w >> 24;
     m.hdr = r[R_HDR * 32];
-    m.blank_shade = r[R_MISC * 32] & 0xFF;
+    w = r[R_MISC * 32];
+    m.blank_shade = w & 0xFF;
+    m.defer_from = m.defer_next = m.defer_active = 0;  // what the last launch left pending (bits 8-23) has been drawn by k_render_pending
     m.n_instr = 0;
     m.n_cycles = 0;
     m.cyc_adj = 0;
@@ -149,7 +156,7 @@ __device__ inline void machine_store(Machine &m, const DevArrays &d, int tile, i
     r[R_MBC * 32] = m.rombank | (m.rambank << 8) | (m.ram_en << 16) | (m.memorymodel << 24);
     r[R_JOY * 32] = m.joy_dir | (m.joy_std << 8) | (((uint32_t)m.ly_window & 0xFF) << 16) | (m.lp_dirty << 24);
     r[R_HDR * 32] = m.hdr;
-    r[R_MISC * 32] = m.blank_shade;
+    r[R_MISC * 32] = m.blank_shade | (m.defer_from << 8) | (m.defer_next << 16);
 }
 
 // ----------------------------------------------------------------------------------- plain memory
@@ -434,6 +441,42 @@ __device__ GB_NOINLINE void fill_framebuffer(uint32_t *fb, uint32_t fill) {
     for (uint32_t k = 0; k < FB_WORDS; k++) fb[k << 5] = fill;
 }
 
+// ---- deferred PPU ----------------------------------------------------------------------------------------------
+// Renderer.scanline reads VRAM, OAM and the scroll / LCDC / palette registers as they are at the HBlank of the line.  The
+// registers are cheap to capture; VRAM and OAM almost never change while a frame is being drawn (games update them in VBlank).
+// So the emulation kernel only RECORDS the lines of the frame it has to render (lcd_record_line) and a second kernel draws
+// them with one thread per (env, line) -- 144 times the parallelism of drawing inside the interpreter thread, whose dependent
+// VRAM loads are pure latency.  Exactness: from the first recorded line of a frame on (defer_active) every write to VRAM / OAM
+// and OAM DMA leaves the fast loop, the slow tick applies the LCD events that are due (recording their lines) and
+// render_flush draws all pending lines from the still unmodified memory BEFORE the write happens.
+#if defined(GB_HOSTSIM)
+static unsigned long long g_hs_flushes = 0, g_hs_flushed_lines = 0;  // host harness only: how often the flush path ran
+#endif
+__device__ GB_NOINLINE void render_flush(Machine &m) {
+#if defined(GB_HOSTSIM)
+    g_hs_flushes++; g_hs_flushed_lines += m.defer_next - m.defer_from;
+#endif
+    for (uint32_t y = m.defer_from; y < m.defer_next; y++) {
+        const uint32_t w0 = m.dl[(y * 3 + 0) << 5], w1 = m.dl[(y * 3 + 1) << 5], w2 = m.dl[(y * 3 + 2) << 5];
+        render_line_out(m.memb, m.fb, w1 & 0xFF, w0, w1 >> 8, (int)w2, y, m.rline, m.rkeys, m.rls);
+    }
+    m.defer_from = m.defer_next = 0;
+}
+
+// HBlank of visible line y on a frame that is rendered, deferred form: capture the renderer's inputs and do its
+// ly_window bookkeeping (render_line: the window line counter advances on every line that shows the window).
+__device__ __forceinline__ void lcd_record_line(Machine &m, uint32_t y) {
+    if (m.defer_from != m.defer_next && m.defer_next != y) render_flush(m);  // lines out of order (LCD switched off and on, LY written)
+    if (m.defer_from == m.defer_next) { m.defer_from = y; }
+    m.dl[(y * 3 + 0) << 5] = m.scroll;
+    m.dl[(y * 3 + 1) << 5] = m.lcdc | (m.pal << 8);
+    m.dl[(y * 3 + 2) << 5] = (uint32_t)m.ly_window;
+    m.defer_next = y + 1;
+    m.defer_active = 1;
+    if ((m.lcdc & 0x20) && M_WY(m) <= y && (int)M_WX(m) - 7 < 160) m.ly_window += 1;
+    if (y == 143) m.ly_window = -1;
+}
+
 __device__ __forceinline__ void lcd_blank_screen(Machine &m) {
     uint32_t shade = pal_shade(M_BGP(m), 0);
     if (m.blank_shade == shade) return;  // already uniformly this shade: the refill would be a no-op
@@ -480,7 +523,8 @@ __device__ inline void lcd_event(Machine &m) {
                     m.lp_dirty--;
                 }
                 if (!m.disable_renderer) {
-                    m.ly_window = render_line_out(m.memb, m.fb, m.lcdc, m.scroll, m.pal, m.ly_window, m.ly, m.rline, m.rkeys, m.rls);
+                    if (m.dl) lcd_record_line(m, m.ly);
+                    else m.ly_window = render_line_out(m.memb, m.fb, m.lcdc, m.scroll, m.pal, m.ly_window, m.ly, m.rline, m.rkeys, m.rls);
                     m.blank_shade = 0xFF;
                 }
             }
@@ -494,6 +538,7 @@ __device__ inline void lcd_event(Machine &m) {
             if (m.ly == 144) {
                 irq |= IRQ_VBLANK;
                 m.frame_done = 1;
+                m.defer_active = 0;  // the frame's pending lines are drawn after the kernel (or at the start of its next frame)
             }
             if (m.ly == 153) m.next_mode = 2;
             break;
@@ -503,6 +548,7 @@ __device__ inline void lcd_event(Machine &m) {
         m.frame_done = 1;
         m.cyc_adj += m.clock - m.clock % FRAME_CYCLES;
         m.clock %= FRAME_CYCLES;
+        m.defer_from = m.defer_next = m.defer_active = 0;  // whatever was pending is painted over
         lcd_blank_screen(m);
     }
 }
@@ -529,6 +575,9 @@ __device__ GB_NOINLINE int lcd_deadline(Machine &m) {
     return t;
 #endif
     const uint32_t nm = m.next_mode, ly = m.ly;
+    // no line of this frame needs the renderer at its HBlank: rendering is off, or the lines are only recorded (deferred PPU; the
+    // first one of a frame is still a hard event: it arms defer_active, which sends VRAM / OAM writes through the slow tick)
+    const bool no_draw = m.disable_renderer || (m.dl && m.defer_active);
     int d;
     if (nm == 1) {
         if (ly == 143) return t;           // the next event enters VBlank
@@ -537,19 +586,19 @@ __device__ GB_NOINLINE int lcd_deadline(Machine &m) {
         // aligned (lcd_event); otherwise stop there.
         const int wrap = t + 456 * (int)(153 - ly);
         if ((m.target + 456u * (153 - ly)) % FRAME_CYCLES != 0) { m.lazy = 1; return wrap; }
-        d = m.disable_renderer ? wrap + 456 * 144 : wrap + 250;
+        d = no_draw ? wrap + 456 * 144 : wrap + 250;
     } else if (nm == 2) {
         if (ly == 153) {
             if (m.target % FRAME_CYCLES != 0) return t;
-            d = m.disable_renderer ? t + 456 * 144 : t + 250;
+            d = no_draw ? t + 456 * 144 : t + 250;
         } else {
             if (ly > 142) return t;
-            d = m.disable_renderer ? t + 456 * (int)(143 - ly) : t + 250;
+            d = no_draw ? t + 456 * (int)(143 - ly) : t + 250;
         }
     } else {
         if (ly > 143) return t;
         const int to_hblank = nm == 3 ? t + 170 : t;  // mode 2 -> 3 -> 0
-        d = m.disable_renderer ? to_hblank + 206 + 456 * (int)(143 - ly) : to_hblank;
+        d = no_draw ? to_hblank + 206 + 456 * (int)(143 - ly) : to_hblank;
     }
     m.lazy = 1;
     return d;
@@ -564,14 +613,19 @@ __device__ GB_NOINLINE void lcd_catch_up(Machine &m) {
     const uint32_t lazy = m.lazy;
     while ((int)(m.clock - m.target) >= 0) {
         const uint32_t behind = m.clock - m.target;
-        if (lazy && m.disable_renderer && m.stat_mode == 0 && m.next_mode == 2 && m.ly < 142 && behind >= 456) {
-            // whole visible lines without rendering: mode 2 / 3 / 0 of each only move LY, STAT, clock_target and the saved
-            // scanline parameters -- closed form for k lines, staying below line 143 (whose HBlank arms the VBlank entry)
+        const bool recording = !m.disable_renderer && m.dl && m.defer_active;
+        if (lazy && (m.disable_renderer || recording) && m.stat_mode == 0 && m.next_mode == 2 && m.ly < 142 && behind >= 456) {
+            // whole visible lines without drawing: mode 2 / 3 / 0 of each only move LY, STAT, clock_target, the saved scanline
+            // parameters and (deferred PPU) the line records -- closed form for k lines, staying below line 143 (whose HBlank
+            // arms the VBlank entry)
             uint32_t k = behind / 456;
             if (k > 142 - m.ly) k = 142 - m.ly;
-            for (uint32_t y = m.ly + 1; m.lp_dirty && y <= m.ly + k; y++) {
-                m.lp[y << 5] = make_uint2(m.scroll, m.lcdc);
-                m.lp_dirty--;
+            for (uint32_t y = m.ly + 1; y <= m.ly + k && (m.lp_dirty || recording); y++) {
+                if (m.lp_dirty) {
+                    m.lp[y << 5] = make_uint2(m.scroll, m.lcdc);
+                    m.lp_dirty--;
+                }
+                if (recording) lcd_record_line(m, y);
             }
             m.ly += k;
             m.stat = (m.stat & 0xF8) | (m.lyc == m.ly ? 0x04 : 0);
@@ -735,14 +789,17 @@ __device__ GB_NOINLINE void bus_write_rare(Machine *mp, uint32_t a, uint32_t v) 
 __device__ __forceinline__ void bus_write_full(Machine &m, uint32_t a, uint32_t v) {  // Motherboard.setitem
     v &= 0xFF;
     if (a - 0xC000u < 0x3E00u) { mem_wr(m, MEM_WRAM + (a & 0x1FFF), v); return; }
-    if ((a >= 0xFF80 && a != 0xFFFF) || (a >= 0xFE00 && a < 0xFF00)) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }
+    if (a >= 0xFF80 && a != 0xFFFF) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }
+    // deferred PPU: recorded lines are drawn from VRAM / OAM as they are NOW, before this write changes them
+    if (m.defer_from != m.defer_next && (a - 0x8000u < 0x2000u || a - 0xFE00u < 0x100u || a == 0xFF46u)) render_flush(m);
+    if (a >= 0xFE00 && a < 0xFF00) { mem_wr(m, MEM_HI + (a - 0xFE00), v); return; }
     if (a - 0x8000u < 0x2000u) { mem_wr(m, MEM_VRAM + (a - 0x8000), v); return; }
     bus_write_rare(&m, a, v);
 }
 __device__ __forceinline__ void bus_write(Machine &m, uint32_t a, uint32_t v) {  // wrapper kernels / debug access
     v &= 0xFF;
     if (a >= 0xC000 && a < 0xE000) mem_wr(m, MEM_WRAM + (a - 0xC000), v);
-    else bus_write_rare(&m, a, v);
+    else bus_write_full(m, a, v);
 }
 
 // ------------------------------------------------------------------------------------------- SM83

@@ -3,13 +3,14 @@
 #include "gb_cpu.cuh"
 #include "gb_device.cuh"
 
-// 64-thread blocks; the register budget (64) lets 16 of them share an SM, i.e. 32 resident warps: the interpreter is a
-// chain of dependent instructions, so throughput below ~60k envs is set by how many warps the schedulers can rotate.
+// 64-thread blocks, 12 of them per SM: an 80-register budget (at 64 registers the loop-entry paths spill the machine pointer and
+// the barrier state: 610 k vs 629 k env-steps/s at 32,768 envs) and 24 resident warps per SM -- the lanes policy (gbenv.cu) never
+// asks for more than 16 per SM below 113k envs.
 #ifndef STEP_THREADS
 #define STEP_THREADS 64
 #endif
 #ifndef STEP_MIN_BLOCKS
-#define STEP_MIN_BLOCKS 16
+#define STEP_MIN_BLOCKS 12
 #endif
 
 // pyboy_binding.ACTIONS (:40) Down Left Right Up A B Start Select -> joypad button ids
@@ -24,6 +25,7 @@ struct RunParams {
     int render_mode;  // 0: renderer disabled, 1: enabled on every frame, 2: enabled on the last frame only
     int release_frame;  // frame index at which the button is released (8 in the reference)
     int lanes;          // envs per warp (1..32): fewer lanes = more warps = more latency hiding
+    int defer;          // deferred PPU: record the lines of the rendered frame (d.dl), k_render_pending draws them
     uint32_t bank_mask;  // rom_banks - 1 when the bank count is a power of two, else 0
     unsigned long long *counters;  // [0] instructions, [1] cycles, [2] frames, [3] faults
 };
@@ -48,6 +50,7 @@ __device__ __forceinline__ void run_frames_env(Machine &m, const RunParams &p, i
     cx.rom_dec = p.d.rom_dec;
     cx.bank_mask = p.bank_mask;
     for (int frame = 0; frame < p.n_frames; frame++) {
+        if (m.defer_from != m.defer_next) render_flush(m);  // deferred lines of the frame before (every frame is rendered: tick)
         // PyBoy.tick applies queued inputs before Motherboard.tick
         if (button >= 0) {
             if (frame == 0) joypad_event(m, button, 1);
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
     Machine &m = slot.m;
     machine_load(m, p.d, tile, lane);
     m.rline = line; m.rkeys = keys; m.rls = nslots;
+    if (p.defer && p.d.dl) m.dl = p.d.dl + il_index(tile, DL_WORDS, 0, lane);
     const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
     run_frames_env<true>(m, p, button);
     machine_store(m, p.d, tile, lane);
@@ -106,7 +110,10 @@ __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS) k_run_frames(Ru
 // up to 32 blocks x 148 SMs = 4,736 envs in one wave).  With __launch_bounds__(1) ptxas knows that no branch can diverge and
 // emits none of the convergence-barrier scaffolding (BSSY / BSYNC / BREAK / BMOV: about one instruction in nine of the
 // multi-lane build's hot loop), keeps loop-invariant addresses in uniform registers and needs no spills.
-__global__ void __launch_bounds__(1, 32) k_run_frames_1(RunParams p) {
+#ifndef STEP1_MIN_BLOCKS
+#define STEP1_MIN_BLOCKS 32
+#endif
+__global__ void __launch_bounds__(1, STEP1_MIN_BLOCKS) k_run_frames_1(RunParams p) {
     const int env = blockIdx.x;
     if (env >= p.d.n_envs || (p.skip && p.skip[env])) return;
     const int tile = env >> 5, lane = env & 31;
@@ -115,6 +122,7 @@ __global__ void __launch_bounds__(1, 32) k_run_frames_1(RunParams p) {
     Machine &m = slot.m;
     machine_load(m, p.d, tile, lane);
     m.rline = line; m.rkeys = keys; m.rls = 1;
+    if (p.defer && p.d.dl) m.dl = p.d.dl + il_index(tile, DL_WORDS, 0, lane);
     const int button = p.actions ? c_action_button[p.actions[env] & 7] : -1;
     run_frames_env<false>(m, p, button);
     machine_store(m, p.d, tile, lane);
@@ -123,6 +131,40 @@ __global__ void __launch_bounds__(1, 32) k_run_frames_1(RunParams p) {
         atomicAdd(&p.counters[1], (unsigned long long)m.n_cycles);
         atomicAdd(&p.counters[2], (unsigned long long)p.n_frames);
     }
+}
+#endif
+
+// Deferred PPU, second half: draws the lines an env's emulation left recorded (R_MISC: [defer_from, defer_next)).
+// `y0`, `dy`: this caller's share of the lines (the kernel: one line per thread; the host harness: all of them).  Returns whether the
+// env had pending lines.
+__device__ __forceinline__ bool render_pending_lines(const DevArrays &d, int tile, int lane, uint32_t y0, uint32_t dy, uint32_t *line, uint32_t *keys, uint32_t ls) {
+    const uint32_t misc = d.regs[il_index(tile, R_WORDS, R_MISC, lane)], from = (misc >> 8) & 0xFF, next = (misc >> 16) & 0xFF;
+    if (from >= next) return false;
+    Machine r;
+    machine_bind(r, d, tile, lane);
+    const uint32_t *dl = d.dl + il_index(tile, DL_WORDS, 0, lane);
+    for (uint32_t y = y0; y < next; y += dy) {
+        if (y < from) continue;
+        const uint32_t w0 = dl[(y * 3 + 0) << 5], w1 = dl[(y * 3 + 1) << 5], w2 = dl[(y * 3 + 2) << 5];
+        r.scroll = w0; r.lcdc = w1 & 0xFF; r.pal = w1 >> 8; r.ly_window = (int)w2;
+        render_line(r, y, line, keys, ls);
+    }
+    return true;
+}
+
+#if !defined(GB_HOSTSIM)
+// grid (tiles, 144 / RENDER_LINES_PER_BLOCK), block (32, RENDER_LINES_PER_BLOCK): x = env (coalesced, as everywhere), one
+// line per thread.  Small blocks on purpose: they have to find room on SMs that another env group's emulation kernel
+// occupies.  The pending range stays in R_MISC; the env's next emulation launch starts from an empty one (machine_load),
+// and an env that is skipped meanwhile (gbenv_step_masked) is skipped here as well.
+#define RENDER_LINES_PER_BLOCK 4
+__global__ void __launch_bounds__(32 * RENDER_LINES_PER_BLOCK) k_render_pending(DevArrays d, const uint8_t *skip) {
+    // the line buffer and the sprite sort keys are thread-local (L1-resident local memory), NOT shared memory: a kernel that
+    // wants a different shared-memory carve-out cannot share an SM with the other group's emulation kernel
+    uint32_t line[FB_LINE_WORDS], keys[10];
+    const int tile = blockIdx.x, lane = threadIdx.x, env = tile * GB_TILE + lane;
+    if (env >= d.n_envs || (skip && skip[env])) return;
+    render_pending_lines(d, tile, lane, blockIdx.y * RENDER_LINES_PER_BLOCK + threadIdx.y, 144, line, keys, 1);
 }
 #endif
 

@@ -32,6 +32,12 @@
 //     word0 = SCX | SCY<<8 | WX<<16 | WY<<24     word1 = LCDC (tile_data_select = bit 4)
 #define LP_WORDS (144 * 2)
 
+// --- deferred-line records (gb_device.cuh "deferred PPU"): what Renderer.scanline needs besides VRAM / OAM, captured at the
+//     HBlank of each visible line of the frame that is rendered: word0 = SCX | SCY<<8 | WX<<16 | WY<<24, word1 = LCDC | BGP<<8 |
+//     OBP0<<16 | OBP1<<24, word2 = Renderer.ly_window before the line.  Scratch between k_run_frames and k_render_pending,
+//     not part of the env's state image.
+#define DL_WORDS (144 * 3)
+
 // --- CPU / LCD / timer / MBC / joypad registers, one word each (see struct Regs in gb_device.cuh)
 enum {
     R_BCDE = 0,   // C | B<<8 | E<<16 | D<<24
@@ -49,7 +55,7 @@ enum {
     R_MBC,        // rombank | rambank<<8 | ram_enabled<<16 | memorymodel<<24
     R_JOY,        // directional | standard<<8 | (ly_window & 0xFF)<<16 | lp_dirty<<24
     R_HDR,        // bootrom_enabled | key1<<8 | double_speed<<16 | cgb<<24
-    R_MISC,       // blank_shade (0..3, 0xFF = framebuffer not uniformly blank)
+    R_MISC,       // blank_shade (0..3, 0xFF = framebuffer not uniformly blank) | defer_from<<8 | defer_next<<16 (lines awaiting k_render_pending)
     R_WORDS
 };
 
@@ -67,6 +73,7 @@ struct DevArrays {
     uint32_t *fb;    // [tiles][FB_WORDS][32]
     uint32_t *lp;    // [tiles][LP_WORDS][32]
     uint32_t *regs;  // [tiles][R_WORDS][32]
+    uint32_t *dl;    // [tiles][DL_WORDS][32]; may be null (no deferred rendering)
     const uint8_t *rom;
     const uint4 *rom_dec;  // pre-decoded ROM: one 16-byte control word per ROM offset (gb_predecode.h)
     uint32_t rom_banks;

@@ -56,6 +56,7 @@ struct gbenv {
     bool ev_valid = false;
     unsigned long long launches = 0;
     int lanes = 32;  // envs per warp in k_run_frames
+    int defer = 1;   // deferred PPU (GBENV_DEFER=0: draw inside the emulation kernel)
     size_t smem_opted = 48 * 1024;
     int32_t *pool_err_host = nullptr;  // pinned copy of WrapArrays.ctl[CTL_ERROR], refreshed asynchronously after every step / reset
     int32_t *d_cm_dense = nullptr;     // staging for gbenv_counts_map
@@ -151,7 +152,7 @@ extern "C" int gbenv_destroy(gbenv *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto &t : h->templates) cudaFree(t.d_image);
-    cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree((void *)h->d.rom); cudaFree((void *)h->d.rom_dec);
+    cudaFree(h->d.mem); cudaFree(h->d.cram); cudaFree(h->d.fb); cudaFree(h->d.lp); cudaFree(h->d.regs); cudaFree(h->d.dl); cudaFree((void *)h->d.rom); cudaFree((void *)h->d.rom_dec);
     cudaFree(h->w.state); cudaFree(h->w.vis_pt); cudaFree(h->w.vis_pool); cudaFree(h->w.vis_free); cudaFree(h->w.cm_dir); cudaFree(h->w.cm_pool);
     cudaFree(h->w.ctl);
     if (h->pool_err_host) cudaFreeHost(h->pool_err_host);
@@ -215,6 +216,7 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
     ALLOC(h->d.cram, T * CRAM_WORDS);
     ALLOC(h->d.fb, T * FB_WORDS);
     ALLOC(h->d.lp, T * LP_WORDS);
+    ALLOC(h->d.dl, T * DL_WORDS);  // deferred-line records (scratch between k_run_frames and k_render_pending)
     ALLOC(h->d.regs, T * R_WORDS);
     uint8_t *d_rom = nullptr;
     ALLOC(d_rom, rom_len + 16);  // padded: the instruction fetch reads two aligned words
@@ -229,7 +231,7 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
         // at once (one wave: SMs x STEP_MIN_BLOCKS blocks) and no more; GBENV_LANES / gbenv_set_lanes_per_warp override.
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id);
-        const int resident_warps = sms * STEP_MIN_BLOCKS * (STEP_THREADS / 32);
+        const int resident_warps = sms * 32;  // warp slots the policy was tuned with (16 two-warp blocks per SM; 32 single-thread blocks)
         // measured on B200 (tools/quick_bench.sh): the smallest power of two that keeps every warp resident wins; counts
         // that are not powers of two make warps straddle 32-env tiles (partial 128-byte lines) and lose 3-5 %
         // and past one env per warp, the next power of two (half a wave of warps) wins: 8,192 envs 198 k env-steps/s at 4
@@ -242,6 +244,7 @@ static int create_impl(gbenv *&h, int n_envs, const uint8_t *rom_host, size_t ro
             if (v >= 1 && v <= 32) lanes = v;
         }
         h->lanes = lanes;
+        if (const char *ev = getenv("GBENV_DEFER")) h->defer = atoi(ev) != 0;
     }
     ALLOC(h->w.state, sizeof(WrapState) * (size_t)n_envs);
     {   // exploration storage (gb_wrap.cuh): page tables / directories per env, pages and blocks from shared pools.  A pool
@@ -402,6 +405,15 @@ extern "C" int gbenv_save_state(gbenv *h, int env, uint8_t *blob) {
 
 // ------------------------------------------------------------------------------- emulator
 
+// deferred PPU, second half: the lines the emulation kernel recorded are drawn with one thread per (env, line slot)
+static int launch_render(gbenv *h, const RunParams &p, cudaStream_t st) {
+    if (!p.defer) return GBENV_OK;
+    k_render_pending<<<dim3(h->n_tiles, 144 / RENDER_LINES_PER_BLOCK), dim3(32, RENDER_LINES_PER_BLOCK), 0, st>>>(p.d, p.skip);
+    h->launches++;
+    CK(cudaGetLastError());
+    return GBENV_OK;
+}
+
 static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int render_mode, cudaStream_t st, const uint8_t *skip_dev = nullptr) {
     RunParams p;
     p.d = h->d;
@@ -412,12 +424,13 @@ static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int re
     p.release_frame = 8;
     p.counters = h->d_counters;
     p.lanes = h->lanes;
+    p.defer = h->defer && render_mode != 0;
     p.bank_mask = (h->d.rom_banks & (h->d.rom_banks - 1)) == 0 ? h->d.rom_banks - 1 : 0;
     if (h->lanes == 1 && !getenv("GBENV_NO_SINGLE")) {  // one env per warp: the single-thread-block build of the same kernel
         k_run_frames_1<<<h->n, 1, ENV_SMEM_BYTES(1), st>>>(p);
         h->launches++;
         CK(cudaGetLastError());
-        return GBENV_OK;
+        return launch_render(h, p, st);
     }
     int warps = (h->n + h->lanes - 1) / h->lanes;
     int blocks = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
@@ -429,7 +442,7 @@ static int launch_run(gbenv *h, const uint8_t *actions_dev, int n_frames, int re
     k_run_frames<<<blocks, STEP_THREADS, smem, st>>>(p);
     h->launches++;
     CK(cudaGetLastError());
-    return GBENV_OK;
+    return launch_render(h, p, st);
 }
 
 extern "C" int gbenv_run_action(gbenv *h, const uint8_t *actions_dev, int frame_skip, void *stream) {

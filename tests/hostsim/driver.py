@@ -33,6 +33,11 @@ class HostSim:
         self.h = self.dll.hs_create(n, rom, len(rom))
         self.dll.hs_set_simt.argtypes = [C.c_void_p, C.c_int]
         self.dll.hs_set_simt(self.h, 1 if simt else 0)  # which build of the fast loop: k_run_frames (SIMT) or k_run_frames_1
+        self.dll.hs_set_defer.argtypes = [C.c_void_p, C.c_int]
+
+    def set_defer(self, on: bool):
+        """deferred PPU on (the product's default) or off (lines drawn inside the frame loop)"""
+        self.dll.hs_set_defer(self.h, 1 if on else 0)
 
     def close(self):
         if self.h:

@@ -31,11 +31,12 @@ extern "C" size_t hs_slots(unsigned long long *out, size_t cap) {
 struct HostSim {
     int n = 0, n_tiles = 0;
     DevArrays d{};
-    std::vector<uint32_t> mem, cram, fb, lp, regs;
+    std::vector<uint32_t> mem, cram, fb, lp, regs, dl;
     std::vector<uint8_t> rom;
     std::vector<uint4> rom_dec;
     unsigned long long counters[4] = {0, 0, 0, 0};
     bool simt = true;  // which build of the fast loop hs_run steps (hs_set_simt)
+    bool defer = true;  // deferred PPU (hs_set_defer): record lines in the frame loop, draw them afterwards like k_render_pending
 };
 
 static void scatter_image(HostSim *h, int env, const std::vector<uint32_t> &img, int version) {
@@ -55,10 +56,10 @@ void *hs_create(int n, const uint8_t *rom, size_t rom_len) {
     h->n_tiles = (n + GB_TILE - 1) / GB_TILE;
     size_t T = (size_t)h->n_tiles * GB_TILE;
     h->mem.assign(T * MEM_WORDS, 0); h->cram.assign(T * CRAM_WORDS, 0); h->fb.assign(T * FB_WORDS, 0);
-    h->lp.assign(T * LP_WORDS, 0); h->regs.assign(T * R_WORDS, 0);
+    h->lp.assign(T * LP_WORDS, 0); h->regs.assign(T * R_WORDS, 0); h->dl.assign(T * DL_WORDS, 0);
     h->rom.assign(rom, rom + rom_len);
     h->rom.resize(rom_len + 16, 0);
-    h->d.mem = h->mem.data(); h->d.cram = h->cram.data(); h->d.fb = h->fb.data(); h->d.lp = h->lp.data(); h->d.regs = h->regs.data();
+    h->d.mem = h->mem.data(); h->d.cram = h->cram.data(); h->d.fb = h->fb.data(); h->d.lp = h->lp.data(); h->d.regs = h->regs.data(); h->d.dl = h->dl.data();
     h->d.rom = h->rom.data();
     h->d.rom_banks = (uint32_t)(rom_len / 0x4000);
     h->d.n_envs = n; h->d.n_tiles = h->n_tiles;
@@ -76,6 +77,8 @@ void *hs_create(int n, const uint8_t *rom, size_t rom_len) {
 
 void hs_destroy(void *p) { delete (HostSim *)p; }
 void hs_set_simt(void *p, int simt) { ((HostSim *)p)->simt = simt != 0; }
+void hs_flush_stats(unsigned long long *out) { out[0] = g_hs_flushes; out[1] = g_hs_flushed_lines; }
+void hs_set_defer(void *p, int defer) { ((HostSim *)p)->defer = defer != 0; }
 
 int hs_load_blob(void *p, int env, const uint8_t *blob, size_t len) {
     HostSim *h = (HostSim *)p;
@@ -100,7 +103,7 @@ int hs_save_blob(void *p, int env, uint8_t *out) {
 int hs_run(void *p, const uint8_t *actions, int n_frames, int render_mode) {
     HostSim *h = (HostSim *)p;
     RunParams rp;
-    rp.d = h->d; rp.actions = actions; rp.skip = nullptr; rp.n_frames = n_frames; rp.render_mode = render_mode; rp.release_frame = 8; rp.lanes = 1;
+    rp.d = h->d; rp.actions = actions; rp.skip = nullptr; rp.n_frames = n_frames; rp.render_mode = render_mode; rp.release_frame = 8; rp.lanes = 1; rp.defer = h->defer && render_mode != 0;
     rp.bank_mask = (h->d.rom_banks & (h->d.rom_banks - 1)) == 0 ? h->d.rom_banks - 1 : 0;
     rp.counters = h->counters;
     for (int env = 0; env < h->n; env++) {
@@ -110,10 +113,17 @@ int hs_run(void *p, const uint8_t *actions, int n_frames, int render_mode) {
         machine_load(slot.m, rp.d, env >> 5, env & 31);
         const int button = actions ? c_action_button[actions[env] & 7] : -1;
         slot.m.rline = line; slot.m.rkeys = keys; slot.m.rls = 1;
+        if (rp.defer) slot.m.dl = rp.d.dl + il_index(env >> 5, DL_WORDS, 0, env & 31);
         if (h->simt) run_frames_env<true>(slot.m, rp, button);
         else run_frames_env<false>(slot.m, rp, button);
         machine_store(slot.m, rp.d, env >> 5, env & 31);
         h->counters[0] += slot.m.n_instr; h->counters[1] += slot.m.n_cycles; h->counters[2] += n_frames;
+    }
+    if (rp.defer) {  // k_render_pending
+        for (int env = 0; env < h->n; env++) {
+            uint32_t line[FB_LINE_WORDS], keys[10];
+            render_pending_lines(rp.d, env >> 5, env & 31, 0, 1, line, keys, 1);
+        }
     }
     return 0;
 }

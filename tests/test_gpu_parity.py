@@ -328,3 +328,48 @@ def test_paged_exploration_storage_many_maps(cuda_lib, oracle_lib, roms, monkeyp
     if not tiny_failed:
         with pytest.raises(_capi.GbEnvError, match="heat-map block pool"):
             tiny.check()
+
+
+def test_deferred_ppu_matches_inline_and_oracle(cuda_lib, oracle_lib, roms, monkeypatch):
+    """Deferred PPU (k_run_frames records the lines of the rendered frame, k_render_pending draws them; a VRAM / OAM write
+    in between flushes first) against the same library with GBENV_DEFER=0 (lines drawn inside the emulation kernel) and
+    against the oracle, on the LCD-observation ROM (VRAM / OAM / scroll / LCDC / LY writes in the middle of frames), through
+    gbenv_step_masked: an env that is skipped keeps its framebuffer -- its stale pending range must not be drawn again."""
+    import torch
+
+    n, steps = 40, 24
+    rom = roms("lcd_probe")
+    monkeypatch.setenv("GBENV_DEFER", "1")
+    deferred = _capi.Handle(cuda_lib, n, rom, 0)
+    monkeypatch.setenv("GBENV_DEFER", "0")
+    inline = _capi.Handle(cuda_lib, n, rom, 0)
+    monkeypatch.delenv("GBENV_DEFER")
+    cpu = _capi.Handle(oracle_lib, n, rom)
+    hs = (deferred, inline, cpu)
+    for h in hs:
+        h.tick(5, True)  # every frame rendered: the lines of frame k are flushed at the start of frame k + 1
+    dev = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    bufs = []
+    for h in hs:
+        gpu = h is not cpu
+        o, r, d = np.zeros((n, _capi.OBS_BYTES), np.uint8), np.zeros(n), np.zeros(n, np.uint8)
+        bufs.append((dev(o), dev(r), dev(d)) if gpu else (o, r, d))
+        h.reset(bufs[-1][0])
+    rng = np.random.default_rng(77)
+    for s in range(steps):
+        act = rng.integers(0, 8, n).astype(np.uint8)
+        skip = (rng.random(n) < 0.2).astype(np.uint8) if s % 3 == 1 else np.zeros(n, np.uint8)
+        for h, (o, r, d) in zip(hs, bufs):
+            gpu = h is not cpu
+            h.step_masked(dev(act) if gpu else act, dev(skip) if gpu else skip, o, r, d)
+        torch.cuda.synchronize()
+        for k in (0, 1):
+            assert np.array_equal(bufs[k][0].cpu().numpy(), bufs[2][0]), (s, k)
+            assert np.array_equal(bufs[k][1].cpu().numpy(), bufs[2][1]), (s, k)
+        if s % 6 == 5:
+            for e in range(n):
+                a, b, c = deferred.save_state(e), inline.save_state(e), cpu.save_state(e)
+                assert a == c, f"step {s} env {e}: deferred vs oracle {diff_states(c, a)[:6]}"
+                assert b == c, f"step {s} env {e}: inline vs oracle {diff_states(c, b)[:6]}"
+    for h in hs:
+        h.close()

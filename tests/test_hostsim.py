@@ -72,6 +72,36 @@ def test_lazy_lcd_probe_seeds(hostsim, oracle_lib, seed):
     hs.close()
 
 
+@pytest.mark.parametrize("defer", [True, False], ids=["deferred", "inline"])
+@pytest.mark.parametrize("seed", [7, 8, 9])
+def test_deferred_ppu_flushes_before_vram_writes(hostsim, oracle_lib, seed, defer):
+    """Deferred PPU (gb_device.cuh render_flush / lcd_record_line, gb_kernels.cuh render_pending_lines): the lines of the frame
+    that is rendered are only recorded at their HBlank and drawn after the frame loop; a write to VRAM / OAM (or an OAM DMA)
+    while lines are pending must draw them first.  The LCD-observation program writes VRAM, OAM, scroll registers, LCDC and LY in
+    the middle of frames, so the framebuffer (part of every save-state compared here) only matches the oracle -- which draws
+    each line at its HBlank as PyBoy does -- if the flush rule holds.  Both forms of the renderer must agree with it."""
+    import ctypes as C
+
+    rom, n = synth_rom.build_lcd_probe_rom(seed=seed, n_blocks=400), 3
+    hs, cpu = hostsim.HostSim(n, rom), _capi.Handle(oracle_lib, n, rom)
+    hs.set_defer(defer)
+    st = (C.c_ulonglong * 2)()
+    hs.dll.hs_flush_stats(st)
+    before = st[0]
+    hs.tick(4, True)  # every frame rendered: the lines of frame k are flushed at the start of frame k + 1
+    cpu.tick(4, True)
+    _compare(hs, cpu, n, "after 4 rendered frames")
+    rng = np.random.default_rng(seed)
+    for s in range(12):
+        act = rng.integers(0, 8, n).astype(np.uint8)
+        hs.run_action(act)
+        cpu.run_action(act)
+        _compare(hs, cpu, n, f"seed {seed} step {s}")
+    hs.dll.hs_flush_stats(st)
+    assert (st[0] > before) == defer  # the flush path ran (deferred) / was never needed (inline)
+    hs.close()
+
+
 def test_real_states_resume_identically(hostsim, oracle_lib, roms):
     """Reference save-states (committed under tests/golden) loaded into both and stepped."""
     from helpers import GOLDEN

@@ -13,7 +13,8 @@ import __graft_entry__ as g
 E, G = int(sys.argv[1]), int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 lanes = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-lib = _capi.GbEnvLib(g.build_cuda())
+import os
+lib = _capi.GbEnvLib(os.environ.get("GBENV_LIB") or g.build_cuda())
 rom = bench.build_rom("pokelike")
 dev = torch.device("cuda", 0)
 n = E // G
