@@ -573,8 +573,8 @@ def main():
         "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args), "envs_per_gpu": E, "act_freq": 24, "rom": args.rom, "parallelism": f"env-sharded x{world}",
-                   "env_groups": G, "env_groups_note": (f"{G} groups of {E // G} envs step on {G} CUDA streams (pokegym_b200.EnvGroups); the single-group "
-                                                        "figure is legs.main_4096" if G > 1 else "one group"),
+                   "env_groups": G, "env_groups_note": (f"{G} groups of {E // G} envs step on {G} CUDA streams (pokegym_b200.EnvGroups)"
+                                                        + ("; the single-group figure is legs.main_4096" if world == 1 else "") if G > 1 else "one group"),
                    "preroll_steps": args.preroll, "info_allreduces_in_timed_region": reduces,
                    "l2_policy": f"working set {E * (16896 + 5760 + 23040 + 1152) / 1e6:.0f} MB of env state + obs per GPU exceeds the 126 MB L2; no explicit flush"},
         "frames_per_s": 24 * value,

@@ -231,7 +231,8 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     uint32_t wa = 0, wt = 0;  // store address; FAST: its classified target
     // FAST: whatever makes the body decline only sets `declined`; the one exit is in front of the write-back, so every
     // divergent region below is single-entry / single-exit and the lanes of a warp re-converge behind each of them
-    if (FAST && h >= H_RARE) FAST_DECLINE();  // rare opcodes, on-the-fly decode
+    // (rare opcodes and descriptors that could not be pre-decoded carry no operand flags: the fast body finds out in the
+    // handler switch's default case, having changed nothing -- one test less on every other instruction)
     if (w & (PDF_RD | PDF_WR)) {
         wa = (w & PDF_AIMM) ? (d.y & 0xFFFFu) : (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu);
         if (w & PDF_ASP) wa = sp;
@@ -376,7 +377,11 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         rv = (v & imm16 & 0xFF) | (imm16 >> 8);
         wv = rv;
         break;
-    default: {  // H_RARE (never in the fast body): `op` is the opcode
+    default: {  // H_RARE / H_SLOW (never in the fast body): `op` is the opcode
+        if (FAST) {
+            FAST_DECLINE();
+            break;
+        }
         const uint32_t a = (hlaf >> 16) & 0xFF, hl = hlaf & 0xFFFF;
         switch (op) {
         case 0x76: m.halted = 1; mode |= MODE_ATTN | MODE_POST; next_pc = r.pc; break;  // HALT: PC stays on the HALT byte
