@@ -10,8 +10,9 @@ from typing import Callable, Dict, List, Optional
 import numpy as np
 
 
-def _names_from_header() -> List[str]:
-    text = (Path(__file__).resolve().parent.parent / "include" / "gbenv_info.h").read_text()
+def names_from_header(path=None) -> List[str]:
+    """The same list parsed from include/gbenv_info.h (source checkouts only: the test that keeps _info_names.py in step)."""
+    text = Path(path or Path(__file__).resolve().parent.parent / "include" / "gbenv_info.h").read_text()
     body = text[text.index("enum {") : text.index("GBI__END")]
     names: List[str] = []
     for tok in re.findall(r"GBI_([A-Z0-9_]+)(?:\s*=\s*([^,]+))?,", body):
@@ -25,7 +26,8 @@ def _names_from_header() -> List[str]:
     return names
 
 
-INFO_NAMES: List[str] = _names_from_header()
+from ._info_names import INFO_NAMES  # noqa: E402  (generated from include/gbenv_info.h)
+
 INFO_INDEX: Dict[str, int] = {n: i for i, n in enumerate(INFO_NAMES)}
 assert len(INFO_NAMES) <= 72 and INFO_NAMES[0] == "count", INFO_NAMES[:3]
 

@@ -6,7 +6,7 @@ so the layout below was verified against all 264 v9 fixtures of the reference tr
 (SURVEY.md section 8c): every field has a fixed offset and the parser consumes exactly
 142,610 bytes (v9) / 142,586 bytes (v7).
 
-The device-side reset path parses the blob in C++ (csrc/gbenv_host.cpp); this module is the host-side
+The device-side reset path parses the blob in C++ (csrc/gb_image.h: blob_to_image); this module is the host-side
 mirror used by tools and tests (building synthetic states, diffing two states field by field).
 """
 from __future__ import annotations

@@ -56,3 +56,10 @@ def test_missing_library_is_an_error(tmp_path):
 
     with pytest.raises(_capi.GbEnvError, match="no CPU fallback"):
         _capi.GbEnvLib(tmp_path / "libgbenv.so")
+
+
+def test_info_names_module_matches_the_header():
+    """pokegym_b200/_info_names.py is generated from include/gbenv_info.h so that an installed package needs no header."""
+    from pokegym_b200 import info
+
+    assert info.INFO_NAMES == info.names_from_header()
