@@ -565,7 +565,9 @@ def main():
     run_ms = (k0b[0] - k0[0]) / max(1, k0b[1] - k0[1])
     wrap_ms = (k1b[0] - k1[0]) / max(1, k1b[1] - k1[1])
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES_PER_ENV_STEP * (E // G) / (run_ms / 1000.0) / 1e9  # one launch steps one group
+    # one launch steps one group; the G launches of a step run side by side (each lasts run_ms, the step barely longer), so the
+    # rate the machine sustains is the bytes of all G over that duration
+    achieved = ALGO_BYTES_PER_ENV_STEP * (E // G) * G / (run_ms / 1000.0) / 1e9
     counters = recorded_counters()
     instr = c1.instructions - c0.instructions
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -581,11 +583,12 @@ def main():
         "emulated_instr_per_s": instr / (ms / 1000.0) * world,
         "roofline": {"bound": "hbm", "kernel": "k_run_frames", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (counters or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                     "kernel_ms": run_ms, "launches_per_step": G, "envs_per_launch": E // G,
+                     "kernel_ms": run_ms, "launches_per_step": G, "concurrent_launches": G, "envs_per_launch": E // G,
                      "kernel_share_of_step": run_ms / (ms / K) if G == 1 else None, "wrap_kernels_ms": wrap_ms,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * (E // G),
                      "note": "the HBM figure is the prescribed one; the kernel is an interpreter and is bounded by instruction issue, see `issue`"
-                             + ("; the launches of the env groups overlap, so kernel_ms is the duration of one group's launch while the other group's runs beside it" if G > 1 else "")},
+                             + (f"; the {G} launches of a step (one per env group) run concurrently: kernel_ms is the event-timed duration of one of them while the "
+                                f"others run beside it, and `achieved` counts the algorithmic bytes of all {G} over that duration" if G > 1 else "")},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": E, "d2h_bytes_per_step": E * (_capi.OBS_BYTES + 8 + 1),
                 "steps": n_e2e, "api": "gbenv_submit_host / gbenv_fetch_host (pinned host buffers, two steps in flight)"},
         "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
