@@ -82,7 +82,7 @@ __global__ void k_predecode_rom(const uint8_t *rom, uint32_t rom_len, uint4 *out
     if (o >= rom_len) return;
     uint32_t in_bank = o & 0x3FFF;
     if (in_bank >= 0x3FFD) {  // operands would come from another bank: decode at run time
-        out[o] = make_uint4(H_SLOW, 0, 0x32103210u, 0);
+        out[o] = make_uint4(H_SLOW, 0, 0x32103210u, PD_NO_CLASS_W);
         return;
     }
     uint32_t ins = rom[o] | (rom[o + 1] << 8) | (rom[o + 2] << 16);
@@ -205,7 +205,7 @@ __device__ __forceinline__ bool fast_stack_push(uint32_t sp) { return sp - 0xC00
 // Outputs: r (registers incl. pc), rom_off (bank switches), cyc, mode (HALT).
 // FAST && SIMT: `declined` may come in already set (no descriptor could be fetched); the body has no exit in front of the
 // write-back.
-template <bool FAST, bool SIMT>
+template <bool FAST, bool SIMT, int CH = -1, uint32_t CF = 0>
 __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &mode, uint32_t &cyc, uint8_t *memb,
                                          const uint8_t *rom, uint32_t bank_mask, bool declined = false) {
     uint32_t bcde = r.bcde, hlaf = r.hlaf, sp = r.sp;
@@ -225,34 +225,36 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         return bus_read_full(m, a);
     };
     // ---- operand fetch (uniform)
-    const uint32_t w = d.w, h = d.x & 0xFF;
+    // CH >= 0: an instance for ONE class of instruction (gb_classes.inc) -- handler id and operand flags are compile-time
+    // constants, every test on them below folds away; CH < 0: the generic body, both come from the control word
+    const uint32_t w = d.w, wf = CH >= 0 ? CF : d.w, h = CH >= 0 ? (uint32_t)CH : (d.x & 0xFF);
     uint32_t v = gb_prmt(bcde, hlaf, w);  // byte 0 = source register (upper bytes: don't care)
-    if (w & PDF_IMM) v = d.y & 0xFFFFu;
+    if (wf & PDF_IMM) v = d.y & 0xFFFFu;
     uint32_t wa = 0, wt = 0;  // store address; FAST: its classified target
     // FAST: whatever makes the body decline only sets `declined`; the one exit is in front of the write-back, so every
     // divergent region below is single-entry / single-exit and the lanes of a warp re-converge behind each of them
     // (rare opcodes and descriptors that could not be pre-decoded carry no operand flags: the fast body finds out in the
     // handler switch's default case, having changed nothing -- one test less on every other instruction)
-    if (w & (PDF_RD | PDF_WR)) {
-        wa = (w & PDF_AIMM) ? (d.y & 0xFFFFu) : (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu);
-        if (w & PDF_ASP) wa = sp;
+    if (wf & (PDF_RD | PDF_WR)) {
+        wa = (wf & PDF_AIMM) ? (d.y & 0xFFFFu) : (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu);
+        if (wf & PDF_ASP) wa = sp;
         if (FAST && SIMT) {
             // ONE straight-line classification of the address serves the read and the deferred store: plain RAM (work RAM
             // and its echo, VRAM, OAM / 0xFEA0-0xFEFF, HRAM -- Motherboard.getitem / setitem touch nothing else for these)
             // is an offset into this env's interleaved array, ROM a pointer into the shared image; selects, no branches
             uint32_t off;
             const bool plain = fast_plain_offset(wa, off);
-            if (w & PDF_WR) {
+            if (wf & PDF_WR) {
                 wt = plain ? off : (wa - 0x2000u < 0x2000u) ? FAST_WR_BANK : (wa - 0xFF10u < 0x30u) ? FAST_WR_DROP : wa == 0xFF00u ? FAST_WR_P1 : FAST_WR_NONE;
                 if (wt == FAST_WR_NONE) FAST_DECLINE();
                 if ((mode & MODE_DEFER) && (wa - 0x8000u < 0x2000u || wa - 0xFE00u < 0x100u)) FAST_DECLINE();  // render_flush first
             }
-            if (w & PDF_RD) {
+            if (wf & PDF_RD) {
                 // P1 (the byte Interaction.pull left there), SB, SC and 0xFF03 read back from the IO array like plain RAM
                 const bool in_rom = wa < 0x8000u, ok = plain | in_rom | (wa - 0xFF00u < 4u);
                 v = fast_load_u8(in_rom ? rom : memb, in_rom ? wa + (wa >> 14) * rom_off : off, ok, v);
                 if (!ok) declined = true;
-                if (w & PDF_RD16) {  // POP / RET: the second byte, classified the same way
+                if (wf & PDF_RD16) {  // POP / RET: the second byte, classified the same way
                     const uint32_t wb = (wa + 1) & 0xFFFF;
                     uint32_t off2;
                     const bool plain2 = fast_plain_offset(wb, off2), in_rom2 = wb < 0x8000u, ok2 = plain2 | in_rom2 | (wb - 0xFF00u < 4u);
@@ -261,46 +263,46 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
                 }
             }
         } else {  // single-lane build: branches are free (nothing diverges), the first matching region wins
-            if (FAST && (w & PDF_WR)) {
+            if (FAST && (wf & PDF_WR)) {
                 wt = fast_store_target(wa);
                 if (wt == FAST_WR_NONE) FAST_DECLINE();
                 if ((mode & MODE_DEFER) && (wa - 0x8000u < 0x2000u || wa - 0xFE00u < 0x100u)) FAST_DECLINE();  // render_flush first
             }
-            if (w & PDF_RD) {
+            if (wf & PDF_RD) {
                 v = rd8(wa);
-                if (w & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
+                if (wf & PDF_RD16) v |= rd8((wa + 1) & 0xFFFF) << 8;
                 if (FAST && declined) return false;
             }
         }
     }
     // ---- handler
     const uint32_t imm16 = d.y & 0xFFFFu, op = gb_prmt(d.x, 0, 0x4441), ex = gb_prmt(d.x, 0, 0x4442), f = hlaf >> 24;
-    uint32_t rv = v, next_pc = d.y >> 16, wv = v, wn = w & PDF_WR;
+    uint32_t rv = v, next_pc = d.y >> 16, wv = v, wn = wf & PDF_WR;
     cyc = d.x >> 24;
 #define PAIR_OPERAND() (gb_prmt(bcde, hlaf, w >> 16) & 0xFFFFu)
     // SIMT: conditional / unconditional jumps are predicated, not dispatched (two selects on every lane), plain moves need no
     // handler at all, and INC / DEC and the ADD ADC SUB SBC CP group share ONE adder body (selects pick the operands): a warp
     // whose lanes run a mix of the four most frequent kinds of instruction takes a single path through here.
     // Single lane: one compare per kind, most frequent first, each with its own minimal body.
-    const bool jump_taken = SIMT && (w & PDF_JUMP) && ((f ^ ex) & op) == 0;
+    const bool jump_taken = SIMT && (wf & PDF_JUMP) && ((f ^ ex) & op) == 0;
     if (SIMT) {
         next_pc = jump_taken ? imm16 : next_pc;
         cyc += jump_taken ? (ex & 0xF) : 0u;
     }
-    if ((w & PDF_MOV) || (SIMT && (w & PDF_JUMP)) || (FAST && SIMT && declined)) {
+    if ((wf & PDF_MOV) || (SIMT && (wf & PDF_JUMP)) || (FAST && SIMT && declined)) {
         // rv = v
-    } else if (!SIMT && (w & PDF_JUMP)) {
+    } else if (!SIMT && (wf & PDF_JUMP)) {
         if (((f ^ ex) & op) == 0) { next_pc = imm16; cyc += ex & 0xF; }
-    } else if (!SIMT && (w & PDF_INCDEC)) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
+    } else if (!SIMT && (wf & PDF_INCDEC)) {  // op = +1 / -1 (mod 256), ex = 0 / N|H: DEC inverts the half carry like a subtraction
         const uint32_t b = v & 0xFF, sum = b + op, res = sum & 0xFF;
         const uint32_t nf = (f & FLAG_C) | ((((b ^ op ^ sum) & 0x10) << 1) ^ ex) | (res == 0 ? FLAG_Z : 0);
         rv = res | (nf << 8);
         wv = res;
-    } else if (w & (PDF_INCDEC | PDF_ARITH)) {
+    } else if (wf & (PDF_INCDEC | PDF_ARITH)) {
         // a + x + cin with  INC / DEC: a = v, x = +1 / -1 (mod 256), no carry in, C kept, ex = 0 / N|H (DEC inverts the half carry
         // like a subtraction);  ADD..CP: a = A, x = v or its complement (ex = 0 / 0xFF), carry in for ADC / SBC (inverted for
         // the subtractions, whose H and C are the inverted carries)
-        const bool inc = SIMT && (w & PDF_INCDEC) != 0;
+        const bool inc = SIMT && (wf & PDF_INCDEC) != 0;
         const uint32_t b = v & 0xFF;
         const uint32_t a = inc ? b : ((hlaf >> 16) & 0xFF), x = inc ? op : (b ^ ex);
         const uint32_t cin = inc ? 0u : ((((f >> 4) & op) ^ ex) & 1);
@@ -338,7 +340,7 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
         break;
     }
     case H_RET: {
-        if (w & PDF_RETI) m.ime = 1;
+        if (wf & PDF_RETI) m.ime = 1;
         if (((f ^ ex) & op) == 0) {
             next_pc = v & 0xFFFF;
             sp = (sp + 2) & 0xFFFF;
@@ -475,6 +477,21 @@ __device__ __forceinline__ bool cpu_exec(Machine &m, const uint4 d, CpuRegs &r, 
     return true;
 }
 
+// Single-lane build: dispatch on the class id of the control word to an instance of the body in which handler and operand
+// flags are constants.  One indexed branch replaces the ~10 flag tests + branches the generic body spends per instruction
+// (12.3 BRA and 17.7 LOP3 of its 68 SASS instructions per emulated one); nothing diverges in a single-thread block, so
+// the code-size price (34 short bodies) is the only one.
+__device__ __forceinline__ bool cpu_exec_by_class(Machine &m, const uint4 d, CpuRegs &r, uint32_t &rom_off, uint32_t &mode, uint32_t &cyc, uint8_t *memb,
+                                                  const uint8_t *rom, uint32_t bank_mask) {
+    switch (PD_CLASS(d.w)) {
+#define GB_CLS(id, H, F) \
+    case id: return cpu_exec<true, false, H, F>(m, d, r, rom_off, mode, cyc, memb, rom, bank_mask);
+#include "gb_classes.inc"
+#undef GB_CLS
+    default: return false;  // rare opcodes, on-the-fly decode: the slow tick
+    }
+}
+
 // The fast body of the lock-step build (k_run_frames, several envs per warp) as ONE straight line of code: no handler
 // dispatch at all.  Every lane computes the result of every kind of instruction the fast set knows -- the adder, the logic
 // unit, the rotator, BIT / RES / SET, CPL, the 16-bit increments and ADD HL, POP's mask, the branch condition -- from its own
@@ -594,7 +611,7 @@ __device__ GB_NOINLINE uint32_t cpu_tick_slow(Machine &m, const uint4 *__restric
     }
     if (execute) {
         const uint32_t pc = m.pc;
-        uint4 d = make_uint4(H_SLOW, 0, 0, 0);
+        uint4 d = make_uint4(H_SLOW, 0, 0, PD_NO_CLASS_W);
         if (pc < 0x8000u) d = __ldg(rom_dec + (pc + (pc >> 14) * m.rom_off));
         if ((d.x & 0xFF) == H_SLOW) d = cpu_decode_slow(m, pc);
         CpuRegs r = {m.bcde, m.hlaf, m.sp, pc};
@@ -637,7 +654,7 @@ again:
             // ONE instance of the instruction body: the descriptor comes from the pre-decoded ROM table or, for the HRAM stub,
             // from an inline decode -- lanes running either kind of code meet again in front of cpu_exec.  SIMT: a lane that
             // has to leave the loop (interrupt pending, HALT, running TIMA, code in other RAM) goes through the body as `declined`.
-            uint4 d = make_uint4(H_SLOW, 0, 0x32103210u, 0);
+            uint4 d = make_uint4(H_SLOW, 0, 0x32103210u, PD_NO_CLASS_W);
             bool leave = false;
             const uint32_t pc = r.pc;
             if (!((pc | mode) & (0x8000u | MODE_POST))) {  // ROM code, nothing pending, not halted, TIMA stopped
@@ -648,15 +665,19 @@ again:
                 if (!SIMT) break;
                 leave = true;
             }
-#if !defined(GB_OPT_LOCKSTEP)  // the fully predicated body lost on B200 (400 k vs 620 k env-steps/s at 32,768 envs): see cpu_exec_lockstep
-            if (!cpu_exec<true, SIMT>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
-#else
             if (SIMT) {
+#if !defined(GB_OPT_LOCKSTEP)  // the fully predicated body lost on B200 (400 k vs 620 k env-steps/s at 32,768 envs): see cpu_exec_lockstep
+                if (!cpu_exec<true, true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
+#else
                 if (!cpu_exec_lockstep(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
-            } else {
-                if (!cpu_exec<true, false>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
-            }
 #endif
+            } else {
+#if defined(GB_OPT_NO_CLASSES)
+                if (!cpu_exec<true, false>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
+#else
+                if (!cpu_exec_by_class(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask)) break;
+#endif
+            }
             GB_TRACE_SLOT(0, pc < 0x8000u ? pc + (pc >> 14) * rom_off : (0xF00000u | pc), d.x, d.w);
             n_instr++;
             rem -= (int)cyc;

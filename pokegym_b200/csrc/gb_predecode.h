@@ -25,9 +25,11 @@
 //                                 the handler's 32-bit result (0x3210 = keep; nibble k = 4 + j puts result byte j
 //                                 into register byte k).  8-bit results travel as res | new_F << 8, so "ADD writes
 //                                 A and F", "CP writes F only" and "INC B writes B and F" differ only in selectors.
-//   w: srcsel | flags << 4 | asel << 16
+//   w: srcsel | flags << 4 | asel << 16 | class << 24
 //        srcsel  PRMT nibble of the 8-bit source register (byte 0..7 of bcde:hlaf)
-//        asel    PRMT selector of the 16-bit address / pair operand (BC 0x10, DE 0x32, HL 0x54, AF-for-PUSH 0x67)
+//        asel    PRMT selector of the 16-bit address / pair operand (BC 0x10, DE 0x32, HL 0x54, AF-for-PUSH 0x67); the class
+//                bits above it select result bytes 2 and 3, which every user masks off
+//        class   dense id of (handler, flags) (gb_classes.inc), 0xFF outside the fast set
 //        flags   PDF_* below
 //
 // Code executed from RAM (the HRAM OAM-DMA stub) and instructions whose operand bytes straddle a 16 KiB bank
@@ -111,13 +113,28 @@ static inline void pd_b_write_pair(pd_builder *b, uint32_t p) {  // rv bytes 0,1
     pd_b_write(b, p * 2, 0);
     pd_b_write(b, p * 2 + 1, 1);
 }
+// Dense id of the (handler, operand flags) pair (gb_classes.inc), 0xFF for whatever the fast set does not know.
+static inline uint32_t pd_class_id(uint32_t h, uint32_t flags) {
+#if !defined(GB_NO_CLASS_LOOKUP)
+#define GB_CLS(id, H, F) \
+    if (h == (H) && flags == (F)) return id;
+#include "gb_classes.inc"
+#undef GB_CLS
+#endif
+    (void)h; (void)flags;
+    return 0xFFu;
+}
+#define PD_CLASS(w) ((w) >> 24)
+#define PD_NO_CLASS_W 0xFF000000u  // w of a control word without flags and outside every class (H_SLOW)
+
 static inline pd_desc_t pd_b_done(const pd_builder *b) {
     pd_desc_t d;
     d.x = b->h | (b->op << 8) | (b->ex << 16) | (b->cyc << 24);
     d.y = (b->imm & 0xFFFFu) | (b->len << 16) | (b->kind << 24);
     d.z = b->sel_lo | (b->sel_hi << 16);
     d.w = (b->srcsel & 0xFu) | (b->flags & 0xFFF0u) | (b->h == H_MOV ? PDF_MOV : 0u) | (b->h == H_JUMP ? PDF_JUMP : 0u) |
-          (b->h == H_INCDEC ? PDF_INCDEC : 0u) | (b->h == H_ARITH ? PDF_ARITH : 0u) | (b->asel << 16);
+          (b->h == H_INCDEC ? PDF_INCDEC : 0u) | (b->h == H_ARITH ? PDF_ARITH : 0u) | ((b->asel & 0xFFu) << 16);
+    d.w |= pd_class_id(b->h, d.w & 0xFFF0u) << 24;
     return d;
 }
 

@@ -76,6 +76,16 @@ void *hs_create(int n, const uint8_t *rom, size_t rom_len) {
 }
 
 void hs_destroy(void *p) { delete (HostSim *)p; }
+// number of per-opcode base descriptors of the fast set without a class id (gb_classes.inc out of date), and the class count
+int hs_class_coverage(int *n_classes) {
+    pd_desc_t t[512];
+    pd_build_base(t);
+    int missing = 0;
+    for (int i = 0; i < 512; i++)
+        if ((t[i].x & 0xFF) < H_RARE && PD_CLASS(t[i].w) >= GB_CLS_COUNT) missing++;
+    *n_classes = GB_CLS_COUNT;
+    return missing;
+}
 void hs_set_simt(void *p, int simt) { ((HostSim *)p)->simt = simt != 0; }
 void hs_flush_stats(unsigned long long *out) { out[0] = g_hs_flushes; out[1] = g_hs_flushed_lines; }
 void hs_set_defer(void *p, int defer) { ((HostSim *)p)->defer = defer != 0; }

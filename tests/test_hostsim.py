@@ -102,6 +102,17 @@ def test_deferred_ppu_flushes_before_vram_writes(hostsim, oracle_lib, seed, defe
     hs.close()
 
 
+def test_every_fast_opcode_has_a_class(hostsim):
+    """gb_classes.inc (tools/gen_classes.sh) lists every (handler, operand flags) pair of the per-opcode base table: the
+    single-lane build dispatches on the class id, and an opcode without one would always take the slow tick."""
+    import ctypes as C
+
+    dll = C.CDLL(str(hostsim.build()))
+    n = C.c_int(0)
+    assert dll.hs_class_coverage(C.byref(n)) == 0
+    assert 30 <= n.value < 255
+
+
 def test_real_states_resume_identically(hostsim, oracle_lib, roms):
     """Reference save-states (committed under tests/golden) loaded into both and stepped."""
     from helpers import GOLDEN
