@@ -634,6 +634,46 @@ __device__ __forceinline__ uint4 cpu_decode_hram(const uint8_t *memb, uint32_t p
     return pd_finish(c_base_desc[(ins & 0xFF) == 0xCB ? (256u | ((ins >> 8) & 0xFF)) : (ins & 0xFF)], ins, pc);
 }
 
+// The fast loop: no call inside (a call in this loop makes the compiler save convergence-barrier state to the stack on
+// every iteration).  Returns true when the countdown has reached the deadline, false when an instruction needs the slow tick.
+// CLASSES (single-lane build only): dispatch on the class id of the control word (cpu_exec_by_class).
+template <bool SIMT, bool CLASSES>
+__device__ __forceinline__ bool cpu_fast_loop(Machine &m, const RunCtx &cx, CpuRegs &r, uint32_t &rom_off, uint32_t &mode, uint32_t &n_instr, int &rem,
+                                              uint8_t *memb, const uint8_t *rom) {
+    for (;;) {
+        uint32_t cyc;
+        // ONE instance of the instruction body: the descriptor comes from the pre-decoded ROM table or, for the HRAM stub,
+        // from an inline decode -- lanes running either kind of code meet again in front of cpu_exec.  SIMT: a lane that
+        // has to leave the loop (interrupt pending, HALT, code in other RAM) goes through the body as `declined`.
+        uint4 d = make_uint4(H_SLOW, 0, 0x32103210u, PD_NO_CLASS_W);
+        bool leave = false;
+        const uint32_t pc = r.pc;
+        if (!((pc | mode) & (0x8000u | MODE_POST))) {  // ROM code, nothing pending, not halted
+            d = __ldg(cx.rom_dec + (pc + (pc >> 14) * rom_off));
+        } else if (!(mode & (MODE_ATTN | MODE_POST)) && pc - 0xFF80u < 0x7Du) {
+            d = cpu_decode_hram(memb, pc);
+        } else {
+            if (!SIMT) return false;
+            leave = true;
+        }
+        if (SIMT) {
+#if !defined(GB_OPT_LOCKSTEP)  // the fully predicated body lost on B200 (400 k vs 620 k env-steps/s at 32,768 envs): see cpu_exec_lockstep
+            if (!cpu_exec<true, true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) return false;
+#else
+            if (!cpu_exec_lockstep(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) return false;
+#endif
+        } else if (CLASSES) {
+            if (!cpu_exec_by_class(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask)) return false;
+        } else {
+            if (!cpu_exec<true, false>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) return false;
+        }
+        GB_TRACE_SLOT(0, pc < 0x8000u ? pc + (pc >> 14) * rom_off : (0xF00000u | pc), d.x, d.w);
+        n_instr++;
+        rem -= (int)cyc;
+        if (rem <= 0) return true;
+    }
+}
+
 // Interprets until this env's LCD clock reaches its next hard event (lcd_deadline).  `m` is the env's machine in shared
 // memory; the SM83 registers, the ROM bank offset, the cycle countdown and the mode word are cached in registers.
 template <bool SIMT>
@@ -647,44 +687,15 @@ __device__ __forceinline__ void cpu_run_to_event(Machine &m, const RunCtx &cx) {
     uint32_t mode = hot_mode(m), timer_pending = 0;
 again:
     do {
-        // ---- fast loop: no call inside (a call in this loop makes the compiler save convergence-barrier state to the
-        // stack on every iteration).  Left when the deadline is reached or an instruction needs the slow tick.
-        for (;;) {
-            uint32_t cyc;
-            // ONE instance of the instruction body: the descriptor comes from the pre-decoded ROM table or, for the HRAM stub,
-            // from an inline decode -- lanes running either kind of code meet again in front of cpu_exec.  SIMT: a lane that
-            // has to leave the loop (interrupt pending, HALT, running TIMA, code in other RAM) goes through the body as `declined`.
-            uint4 d = make_uint4(H_SLOW, 0, 0x32103210u, PD_NO_CLASS_W);
-            bool leave = false;
-            const uint32_t pc = r.pc;
-            if (!((pc | mode) & (0x8000u | MODE_POST))) {  // ROM code, nothing pending, not halted, TIMA stopped
-                d = __ldg(cx.rom_dec + (pc + (pc >> 14) * rom_off));
-            } else if (!(mode & (MODE_ATTN | MODE_POST)) && pc - 0xFF80u < 0x7Du) {
-                d = cpu_decode_hram(memb, pc);
-            } else {
-                if (!SIMT) break;
-                leave = true;
-            }
-            if (SIMT) {
-#if !defined(GB_OPT_LOCKSTEP)  // the fully predicated body lost on B200 (400 k vs 620 k env-steps/s at 32,768 envs): see cpu_exec_lockstep
-                if (!cpu_exec<true, true>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
-#else
-                if (!cpu_exec_lockstep(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
-#endif
-            } else {
-#if defined(GB_OPT_NO_CLASSES)
-                if (!cpu_exec<true, false>(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask, leave)) break;
-#else
-                if (!cpu_exec_by_class(m, d, r, rom_off, mode, cyc, memb, rom, cx.bank_mask)) break;
-#endif
-            }
-            GB_TRACE_SLOT(0, pc < 0x8000u ? pc + (pc >> 14) * rom_off : (0xF00000u | pc), d.x, d.w);
-            n_instr++;
-            rem -= (int)cyc;
-            if (rem <= 0) {
-                timer_pending = 1;
-                goto deadline;
-            }
+        // ---- fast loop (cpu_fast_loop).  The single-lane build has two copies: class-dispatched bodies (34 of them: a large
+        // hot set that pays when the loop runs long) and, while TIMA runs -- the countdown then ends every few instructions and
+        // the loop's entry / exit paths are as hot as its body -- the compact generic one.
+        bool at_deadline;
+        if (!SIMT && !(m.tmr & TIMA_ON)) at_deadline = cpu_fast_loop<SIMT, true>(m, cx, r, rom_off, mode, n_instr, rem, memb, rom);
+        else at_deadline = cpu_fast_loop<SIMT, false>(m, cx, r, rom_off, mode, n_instr, rem, memb, rom);
+        if (at_deadline) {
+            timer_pending = 1;
+            goto deadline;
         }
         {
             // ---- slow tick.  Park the registers, bring the clocks up to date, apply the soft LCD events that have become due
